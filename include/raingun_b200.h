@@ -1,0 +1,212 @@
+/*
+ * raingun_b200.h — C ABI of the B200-native render hot path.
+ *
+ * This is the drop-in boundary for raingun-lib's per-pixel render path. The
+ * reference has no FFI today; the path sits behind two inherent methods of a
+ * plain Rust struct:
+ *
+ *     pub struct Scene { fov, default_color, max_recursion_depth, bodies, lights }
+ *                                                   raingun-lib/src/scene.rs:11-19
+ *     Scene::render_image(&self, w, h) -> ImageBuffer<Rgba<u8>>      scene.rs:41-43
+ *     Scene::streaming_render(&self, w, h, Sender<RenderedPixel>)    scene.rs:45-51
+ *
+ * A host (the Rust `-sys` shim shown in INTEGRATION.md, the C++ host in
+ * raingun_b200/host, or the Python ctypes mirror in raingun_b200/) parses the
+ * YAML scene and decodes textures exactly as the reference does, flattens the
+ * `Vec<Body>` / `Vec<Light>` into the body-indexed arrays of `rg_scene_desc`,
+ * and calls the entry points below.  Plain pointers and sizes only; the library
+ * copies everything it is given (host buffers stay caller-owned).
+ *
+ * There is no CPU fallback: every entry point that renders fails with
+ * RG_E_CUDA when no sm_100 device is usable.
+ */
+#ifndef RAINGUN_B200_H
+#define RAINGUN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RG_ABI_VERSION 1u
+
+/* Largest scene.max_recursion_depth the device path accepts (the reference's
+ * default is 10, scene.rs:26; `--draft` lowers it to 4, src/main.rs:74-75). */
+#define RG_MAX_DEPTH 64u
+/* Largest light count (shadow results are kept in a 32-bit mask per hit). */
+#define RG_MAX_LIGHTS 32u
+
+/* ---- error codes (0 = ok, negative = failure; never unwinds across the ABI) */
+enum {
+    RG_OK = 0,
+    RG_E_INVALID = -1,    /* null pointer, bad enum value, bad index            */
+    RG_E_PORTRAIT = -2,   /* width < height: `assert!(width >= height)` ray.rs:42 */
+    RG_E_TOO_LARGE = -3,  /* width*height does not fit u32 (rendering.rs:27)    */
+    RG_E_DEPTH = -4,      /* max_recursion_depth > RG_MAX_DEPTH                 */
+    RG_E_CUDA = -5,       /* CUDA runtime failure / no usable device            */
+    RG_E_NOMEM = -6,      /* device or host allocation failed                   */
+    RG_E_CANCELLED = -7,  /* streaming callback asked to stop (rendering.rs:53-54,67) */
+    RG_E_LIGHTS = -8      /* more than RG_MAX_LIGHTS lights                     */
+};
+
+/* ---- enums mirroring the reference's serde enums --------------------------- */
+enum { RG_BODY_SPHERE = 0, RG_BODY_PLANE = 1, RG_BODY_DISK = 2, RG_BODY_AABB = 3 }; /* bodies.rs:41-47 */
+enum { RG_COLORATION_COLOR = 0, RG_COLORATION_TEXTURE = 1 };                        /* material.rs:20-24 */
+enum { RG_SURFACE_DIFFUSE = 0, RG_SURFACE_REFLECTING = 1, RG_SURFACE_REFRACTIVE = 2 }; /* material.rs:49-54 */
+enum { RG_LIGHT_DIRECTIONAL = 0, RG_LIGHT_SPHERICAL = 1 };                          /* lights.rs:22-26 */
+
+/* One decoded texture (`DynamicImage`, material.rs:26-32).  `channels` is 3
+ * (RGB8) or 4 (RGBA8); rows are tightly packed, row-major, top row first —
+ * `get_pixel(x, y)` order (material.rs:67). */
+typedef struct rg_texture_desc {
+    uint32_t width;
+    uint32_t height;
+    uint32_t channels;
+    uint32_t reserved;
+    const uint8_t *pixels;
+} rg_texture_desc;
+
+/* The flattened `Scene` (scene.rs:11-19).  All per-body arrays are indexed by
+ * the body's position in `Scene::bodies`, which is what the first-minimum
+ * tie-break of `Scene::trace` (scene.rs:34-39) depends on.
+ *
+ * body_geom[i][8] (f64), by kind:
+ *   SPHERE  center.x,y,z, radius                              bodies.rs:13-18
+ *   PLANE   origin.x,y,z, normal.x,y,z   (normal NOT normalised) bodies.rs:20-25
+ *   DISK    origin.x,y,z, normal.x,y,z, radius                bodies.rs:27-33
+ *   AABB    bounds[0].x,y,z, bounds[1].x,y,z                  bodies.rs:35-39
+ * f32 material fields are the YAML numbers parsed as f64 and then narrowed,
+ * as serde does (material.rs:10,30-31,52-53; lights.rs:12,19).
+ */
+typedef struct rg_scene_desc {
+    uint32_t abi_version;          /* RG_ABI_VERSION */
+    uint32_t max_recursion_depth;  /* scene.rs:16, default 10 */
+    double fov;                    /* degrees, scene.rs:14, default 90 */
+    float default_color[3];        /* scene.rs:15 */
+    uint32_t n_bodies;
+
+    const uint8_t *body_kind;       /* [n_bodies] RG_BODY_*            */
+    const double *body_geom;        /* [n_bodies][8]                   */
+    const uint8_t *coloration_kind; /* [n_bodies] RG_COLORATION_*      */
+    const float *color;             /* [n_bodies][3] (Color variant)   */
+    const int32_t *texture_id;      /* [n_bodies] index into textures, or -1 */
+    const float *texture_offset;    /* [n_bodies][2] x_offset, y_offset */
+    const float *albedo;            /* [n_bodies]                      */
+    const uint8_t *surface_kind;    /* [n_bodies] RG_SURFACE_*         */
+    const float *surface_param;     /* [n_bodies][2]: Reflecting{reflectivity,-};
+                                       Refractive{index, transparency} */
+
+    uint32_t n_lights;
+    uint32_t n_textures;
+    const uint8_t *light_kind;      /* [n_lights] RG_LIGHT_*           */
+    const double *light_vec;        /* [n_lights][3] direction | position */
+    const float *light_color;       /* [n_lights][3]                   */
+    const float *light_intensity;   /* [n_lights]                      */
+
+    const rg_texture_desc *textures; /* [n_textures] */
+} rg_scene_desc;
+
+/* Which device pipeline renders (all are bit-identical in their output). */
+enum {
+    RG_PIPELINE_WAVEFRONT = 0, /* per-bounce ray queues (default)                 */
+    RG_PIPELINE_MEGAKERNEL = 1 /* one thread per pixel, explicit stack (validation) */
+};
+/* How `Scene::trace` is evaluated (results identical). */
+enum {
+    RG_ACCEL_AUTO = 0,  /* grid when it pays, brute force otherwise */
+    RG_ACCEL_BRUTE = 1, /* the reference algorithm: every ray x every body */
+    RG_ACCEL_GRID = 2   /* exact culling through a uniform grid + brute-force rest */
+};
+/* Option keys for rg_scene_set_option. */
+enum {
+    RG_OPT_PIPELINE = 1,
+    RG_OPT_ACCEL = 2,
+    RG_OPT_MAX_DEPTH = 3,    /* like main.rs:119-123: lowers max_recursion_depth  */
+    RG_OPT_BATCH_PIXELS = 4, /* pixels per wavefront batch (0 = automatic)         */
+    RG_OPT_VERIFY_CULL = 5   /* debug: count FP32-culled pairs the FP64 test hits  */
+};
+
+/* Counters and timings of one render call.  A "ray" is one `Scene::trace`
+ * invocation (rendering.rs:73 primary, :126 reflection/transmission, :150 shadow). */
+typedef struct rg_stats {
+    uint64_t rays_primary;
+    uint64_t rays_shadow;
+    uint64_t rays_reflection;
+    uint64_t rays_transmission;
+    uint64_t body_tests;           /* sum over rays of n_bodies (brute-force charge) */
+    uint64_t exact_tests;          /* FP64 intersect evaluations actually executed   */
+    uint64_t cull_unsound;         /* RG_OPT_VERIFY_CULL: must be 0                   */
+    /* conditions on which the reference would have panicked */
+    uint64_t err_nan_distance;     /* scene.rs:38 partial_cmp().unwrap()             */
+    uint64_t err_transmission_none;/* rendering.rs:106 .unwrap() on None             */
+    uint64_t err_aabb_normal;      /* bodies.rs:324 assert!(false)                   */
+    double ms_device;              /* CUDA-event time of all device work             */
+    double ms_trace;               /* ... of the nearest-hit + shadow kernels        */
+    double ms_wall;                /* host wall clock of the call                    */
+    uint32_t gpu_launches;         /* kernels launched by this call                  */
+    uint32_t batches;              /* wavefront batches                              */
+    uint32_t max_level;            /* deepest level that traced a ray                */
+    uint32_t accel_used;           /* RG_ACCEL_BRUTE | RG_ACCEL_GRID                 */
+} rg_stats;
+
+typedef struct rg_scene rg_scene;
+
+/* Streaming callback: one finished band of rows (the analogue of the
+ * `RenderedPixel` messages, rendering.rs:18-22,59-65).  `rgba` holds
+ * `rows * width * 4` bytes and is only valid during the call.  Return 0 to
+ * continue, non-zero to cancel (a closed channel, rendering.rs:53-54,67). */
+typedef int (*rg_rows_cb)(uint32_t y0, uint32_t rows, uint32_t width,
+                          const uint8_t *rgba, void *user);
+
+/* Copies the flattened scene, uploads it to CUDA device `device`, builds the
+ * exact-culling grid.  Replaces the serde construction of `Scene`
+ * (scene.rs:11-31) + `load_texture` (material.rs:34-47) as the upload layer. */
+int rg_scene_create(const rg_scene_desc *desc, int32_t device, rg_scene **out);
+void rg_scene_destroy(rg_scene *scene);
+int rg_scene_set_option(rg_scene *scene, int32_t key, int64_t value);
+
+/* Scene::render_image (scene.rs:41-43 -> rendering.rs:24-38).  Blocking; writes
+ * width*height*4 bytes of row-major RGBA8 (alpha 255, color.rs:32-37) into
+ * caller-owned HOST memory. `stats` may be NULL. */
+int rg_render(rg_scene *scene, uint32_t width, uint32_t height,
+              uint8_t *rgba_out, rg_stats *stats);
+
+/* The same, restricted to image rows [y0, y1): the unit multi-GPU sharding
+ * works in.  Writes (y1-y0)*width*4 bytes. */
+int rg_render_rows(rg_scene *scene, uint32_t width, uint32_t height,
+                   uint32_t y0, uint32_t y1, uint8_t *rgba_out, rg_stats *stats);
+
+/* As rg_render_rows but the result stays in DEVICE memory (`d_rgba_out`, on the
+ * scene's device, (y1-y0)*width*4 bytes) and the work is enqueued on
+ * `cuda_stream` (a cudaStream_t, NULL = the legacy default stream).  The call
+ * returns after the device work has finished (per-level queue sizes are read
+ * back on the host). */
+int rg_render_rows_device(rg_scene *scene, uint32_t width, uint32_t height,
+                          uint32_t y0, uint32_t y1, void *d_rgba_out,
+                          void *cuda_stream, rg_stats *stats);
+
+/* Scene::streaming_render (scene.rs:45-51 -> rendering.rs:40-69): renders in
+ * bands of `band_rows` rows (0 = automatic) and hands each finished band to
+ * `cb` from the calling thread.  Returns RG_E_CANCELLED if `cb` returned
+ * non-zero. */
+int rg_render_stream(rg_scene *scene, uint32_t width, uint32_t height,
+                     uint32_t band_rows, rg_rows_cb cb, void *user, rg_stats *stats);
+
+/* Thread-local description of the last failure in this thread. */
+const char *rg_last_error(void);
+
+/* Roofline denominators measured on the scene-independent device: a register-
+ * resident FFMA / DFMA loop over the whole chip.  Results in TFLOP/s
+ * (2 flops per FMA).  Used by bench.py; not part of the render path. */
+int rg_measure_peaks(int32_t device, double *fp32_tflops, double *fp64_tflops,
+                     double *sm_clock_mhz);
+
+/* Number of usable CUDA devices (0 if none / no driver). */
+int rg_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAINGUN_B200_H */
