@@ -1,0 +1,557 @@
+// rg_api.cu — the C ABI (include/raingun_b200.h): scene upload, render entry points,
+// error reporting.  Host-side hoists are limited to values that are pure functions of the
+// scene and are computed with the reference's own operation order (this file is compiled
+// with -ffp-contract=off on the host side).
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "rg_cull.h"
+#include "rg_host.h"
+#include "rg_mega.cuh"
+
+namespace rg {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        return RG_E_NOMEM;
+    }
+    return RG_E_CUDA;
+}
+
+int DeviceBuffer::reserve(size_t bytes) {
+    if (bytes <= cap) return RG_OK;
+    if (ptr) { cudaFree(ptr); ptr = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;   // headroom: neighbouring frames differ slightly
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&ptr, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess) { ptr = nullptr; return cuda_fail(e, "cudaMalloc(scratch)", __FILE__, __LINE__); }
+    cap = want;
+    return RG_OK;
+}
+void DeviceBuffer::release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+}
+void WavefrontScratch::release() {
+    ray[0].release(); ray[1].release(); hit_t.release(); hit_body.release(); sray.release();
+    s_tmax.release(); s_ab.release(); s_lit.release(); lit_bc.release(); lit_node.release();
+    for (auto &b : nodes) b.release();
+    nodes.clear();
+}
+
+template <typename T>
+static int upload(rg_scene *sc, const T *host, size_t count, const T **out) {
+    *out = nullptr;
+    if (count == 0) return RG_OK;
+    void *p = nullptr;
+    RG_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    sc->owned.push_back(p);
+    RG_CUDA(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<const T *>(p);
+    return RG_OK;
+}
+
+static int validate(const rg_scene_desc *d) {
+    if (!d) { set_error("scene desc is NULL"); return RG_E_INVALID; }
+    if (d->abi_version != RG_ABI_VERSION) { set_error("abi_version %u != %u", d->abi_version, RG_ABI_VERSION); return RG_E_INVALID; }
+    if (d->max_recursion_depth > RG_MAX_DEPTH) { set_error("max_recursion_depth %u > %u", d->max_recursion_depth, RG_MAX_DEPTH); return RG_E_DEPTH; }
+    if (d->n_lights > RG_MAX_LIGHTS) { set_error("%u lights > %u", d->n_lights, RG_MAX_LIGHTS); return RG_E_LIGHTS; }
+    if (d->n_bodies && (!d->body_kind || !d->body_geom || !d->coloration_kind || !d->color || !d->texture_id ||
+                        !d->texture_offset || !d->albedo || !d->surface_kind || !d->surface_param)) {
+        set_error("a per-body array is NULL");
+        return RG_E_INVALID;
+    }
+    if (d->n_lights && (!d->light_kind || !d->light_vec || !d->light_color || !d->light_intensity)) {
+        set_error("a per-light array is NULL");
+        return RG_E_INVALID;
+    }
+    if (d->n_textures && !d->textures) { set_error("textures is NULL"); return RG_E_INVALID; }
+    for (uint32_t i = 0; i < d->n_bodies; ++i) {
+        if (d->body_kind[i] > RG_BODY_AABB) { set_error("bodies[%u]: bad kind %u", i, d->body_kind[i]); return RG_E_INVALID; }
+        if (d->surface_kind[i] > RG_SURFACE_REFRACTIVE) { set_error("bodies[%u]: bad surface %u", i, d->surface_kind[i]); return RG_E_INVALID; }
+        if (d->coloration_kind[i] > RG_COLORATION_TEXTURE) { set_error("bodies[%u]: bad coloration", i); return RG_E_INVALID; }
+        if (d->coloration_kind[i] == RG_COLORATION_TEXTURE &&
+            (d->texture_id[i] < 0 || (uint32_t)d->texture_id[i] >= d->n_textures)) {
+            set_error("bodies[%u]: texture_id %d out of range", i, d->texture_id[i]);
+            return RG_E_INVALID;
+        }
+    }
+    for (uint32_t i = 0; i < d->n_lights; ++i)
+        if (d->light_kind[i] > RG_LIGHT_SPHERICAL) { set_error("lights[%u]: bad kind", i); return RG_E_INVALID; }
+    for (uint32_t i = 0; i < d->n_textures; ++i) {
+        const rg_texture_desc &t = d->textures[i];
+        if (!t.pixels || t.width == 0 || t.height == 0 || (t.channels != 3 && t.channels != 4) ||
+            t.width > 0x7FFFFFFFu || t.height > 0x7FFFFFFFu) {
+            set_error("textures[%u]: bad descriptor", i);
+            return RG_E_INVALID;
+        }
+    }
+    return RG_OK;
+}
+
+// ray.rs:46: (fov.to_radians() / 2.0).tan(); f64::to_radians is `self * (PI / 180.0)`.
+static double fov_adjustment(double fov_degrees) {
+    const double pi = 3.14159265358979323846264338327950288;
+    return std::tan((fov_degrees * (pi / 180.0)) / 2.0);
+}
+
+static int create_textures(rg_scene *sc, const rg_scene_desc *d) {
+    std::vector<DTex> host(d->n_textures);
+    for (uint32_t i = 0; i < d->n_textures; ++i) {
+        const rg_texture_desc &t = d->textures[i];
+        // DynamicImage::get_pixel yields Rgba<u8> (material.rs:67); RGB sources get alpha 255.
+        std::vector<uchar4> rgba((size_t)t.width * t.height);
+        for (size_t p = 0; p < rgba.size(); ++p) {
+            const uint8_t *src = t.pixels + p * t.channels;
+            rgba[p] = make_uchar4(src[0], src[1], src[2], t.channels == 4 ? src[3] : 255);
+        }
+        cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+        cudaArray_t arr = nullptr;
+        RG_CUDA(cudaMallocArray(&arr, &fmt, t.width, t.height));
+        sc->tex_arrays.push_back(arr);
+        RG_CUDA(cudaMemcpy2DToArray(arr, 0, 0, rgba.data(), (size_t)t.width * 4, (size_t)t.width * 4, t.height,
+                                    cudaMemcpyHostToDevice));
+        cudaResourceDesc res{};
+        res.resType = cudaResourceTypeArray;
+        res.res.array.array = arr;
+        cudaTextureDesc td{};
+        td.addressMode[0] = cudaAddressModeClamp;
+        td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;        // nearest texel: material.rs:63-68 does no filtering
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        cudaTextureObject_t obj = 0;
+        RG_CUDA(cudaCreateTextureObject(&obj, &res, &td, nullptr));
+        sc->tex_objs.push_back(obj);
+        host[i].obj = obj;
+        host[i].w = t.width;
+        host[i].h = t.height;
+    }
+    return upload(sc, host.data(), host.size(), &sc->ds.tex);
+}
+
+static int build_scene(rg_scene *sc, const rg_scene_desc *d) {
+    DScene &ds = sc->ds;
+    const uint32_t n = d->n_bodies;
+    ds.n_bodies = n;
+    ds.n_lights = d->n_lights;
+    ds.max_depth = d->max_recursion_depth;
+    sc->scene_max_depth = d->max_recursion_depth;
+    sc->n_bodies = n;
+    ds.fov_adj = fov_adjustment(d->fov);
+    for (int k = 0; k < 3; ++k) ds.default_color[k] = d->default_color[k];
+
+    std::vector<BodyMat> mats(n);
+    std::vector<double> sph;          // n_spheres x 4
+    std::vector<uint32_t> sph_body, misc_body;
+    for (uint32_t i = 0; i < n; ++i) {
+        BodyMat &m = mats[i];
+        std::memset(&m, 0, sizeof(m));
+        for (int k = 0; k < 3; ++k) m.color[k] = d->color[3 * (size_t)i + k];
+        m.albedo = d->albedo[i];
+        m.p0 = d->surface_param[2 * (size_t)i];
+        m.p1 = d->surface_param[2 * (size_t)i + 1];
+        m.tex_off[0] = d->texture_offset[2 * (size_t)i];
+        m.tex_off[1] = d->texture_offset[2 * (size_t)i + 1];
+        m.tex = d->coloration_kind[i] == RG_COLORATION_TEXTURE ? d->texture_id[i] : -1;
+        m.coloration = d->coloration_kind[i];
+        m.surface = d->surface_kind[i];
+        const double *g = d->body_geom + 8 * (size_t)i;
+        if (d->body_kind[i] == RG_BODY_SPHERE) {
+            sph.insert(sph.end(), g, g + 4);
+            sph_body.push_back(i);
+        } else {
+            misc_body.push_back(i);
+        }
+    }
+    ds.n_spheres = (uint32_t)sph_body.size();
+    ds.n_misc = (uint32_t)misc_body.size();
+
+    // FP32 cull records (rg_cull.h).  P = centre of the bounding box of the sphere centres.
+    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    bool have = false;
+    for (uint32_t i = 0; i < ds.n_spheres; ++i) {
+        bool finite = true;
+        for (int k = 0; k < 3; ++k) finite = finite && std::isfinite(sph[4 * (size_t)i + k]);
+        if (!finite) continue;
+        for (int k = 0; k < 3; ++k) {
+            double c = sph[4 * (size_t)i + k];
+            if (!have) { lo[k] = hi[k] = c; }
+            else { lo[k] = std::fmin(lo[k], c); hi[k] = std::fmax(hi[k], c); }
+        }
+        have = true;
+    }
+    for (int k = 0; k < 3; ++k) ds.cull_ref[k] = have ? 0.5 * (lo[k] + hi[k]) : 0.0;
+    std::vector<float4> cull(ds.n_spheres);
+    for (uint32_t i = 0; i < ds.n_spheres; ++i) {
+        double cx = sph[4 * (size_t)i] - ds.cull_ref[0], cy = sph[4 * (size_t)i + 1] - ds.cull_ref[1],
+               cz = sph[4 * (size_t)i + 2] - ds.cull_ref[2], r = sph[4 * (size_t)i + 3];
+        double C2 = cx * cx + cy * cy + cz * cz, r2 = r * r;
+        float4 rec;
+        rec.x = (float)cx; rec.y = (float)cy; rec.z = (float)cz;
+        if (C2 < kCullHuge && r2 < kCullHuge) {   // also false for NaN
+            double K = (C2 - r2) - kCullU * (kCullSphereC2 * C2 + kCullSphereR2 * r2);
+            rec.w = (float)K;
+        } else {
+            rec.x = rec.y = rec.z = 0.0f;
+            rec.w = -std::numeric_limits<float>::infinity();   // never rejected
+        }
+        cull[i] = rec;
+    }
+
+    for (uint32_t l = 0; l < d->n_lights; ++l) {
+        DLight &L = ds.lights[l];
+        L.kind = d->light_kind[l];
+        const double *v = d->light_vec + 3 * (size_t)l;
+        if (L.kind == RG_LIGHT_DIRECTIONAL) {
+            // lights.rs:48: (-directional.direction).normalize(), cgmath order
+            double nx = -v[0], ny = -v[1], nz = -v[2];
+            double inv = 1.0 / std::sqrt((nx * nx + ny * ny) + nz * nz);
+            L.v[0] = nx * inv; L.v[1] = ny * inv; L.v[2] = nz * inv;
+        } else {
+            L.v[0] = v[0]; L.v[1] = v[1]; L.v[2] = v[2];
+        }
+        for (int k = 0; k < 3; ++k) L.color[k] = d->light_color[3 * (size_t)l + k];
+        L.intensity = d->light_intensity[l];
+    }
+
+    int rc;
+    if ((rc = upload(sc, d->body_kind, n, &ds.kind))) return rc;
+    if ((rc = upload(sc, d->body_geom, 8 * (size_t)n, &ds.geom))) return rc;
+    if ((rc = upload(sc, mats.data(), mats.size(), &ds.mat))) return rc;
+    if ((rc = upload(sc, reinterpret_cast<const double4 *>(sph.data()), (size_t)ds.n_spheres, &ds.sph))) return rc;
+    if ((rc = upload(sc, sph_body.data(), sph_body.size(), &ds.sph_body))) return rc;
+    if ((rc = upload(sc, cull.data(), cull.size(), &ds.cull4))) return rc;
+    if ((rc = upload(sc, misc_body.data(), misc_body.size(), &ds.misc_body))) return rc;
+    if ((rc = create_textures(sc, d))) return rc;
+    if ((rc = grid_build(sc, sph))) return rc;
+    return RG_OK;
+}
+
+// ---- roofline denominators: register-resident FMA loops ---------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_fma_peak(T *out, int iters, T a, T b, long long *cycles) {
+    T x0 = (T)threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    long long c0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+        if constexpr (sizeof(T) == 4) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        } else {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    long long c1 = clock64();
+    T s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == (T)123456789) out[0] = s;   // keeps the loop alive, never true in practice
+    if (blockIdx.x == 0 && threadIdx.x == 0 && cycles) *cycles = c1 - c0;
+}
+
+}  // namespace rg
+
+using namespace rg;
+
+extern "C" {
+
+const char *rg_last_error(void) { return g_last_error.c_str(); }
+
+int rg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void rg_scene_destroy(rg_scene *sc) {
+    if (!sc) return;
+    cudaSetDevice(sc->device);
+    for (auto o : sc->tex_objs) cudaDestroyTextureObject(o);
+    for (auto a : sc->tex_arrays) cudaFreeArray(a);
+    for (auto p : sc->owned) cudaFree(p);
+    sc->wf.release();
+    sc->frame.release();
+    if (sc->h_frame) cudaFreeHost(sc->h_frame);
+    if (sc->d_counters) cudaFree(sc->d_counters);
+    if (sc->h_counters) cudaFreeHost(sc->h_counters);
+    for (auto &e : sc->ev) if (e) cudaEventDestroy(e);
+    if (sc->stream) cudaStreamDestroy(sc->stream);
+    delete sc;
+}
+
+int rg_scene_create(const rg_scene_desc *desc, int32_t device, rg_scene **out) {
+    if (!out) { set_error("out is NULL"); return RG_E_INVALID; }
+    *out = nullptr;
+    int rc = validate(desc);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(e));
+        return RG_E_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return RG_E_INVALID; }
+    RG_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    RG_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return RG_E_CUDA;
+    }
+    rg_scene *sc = new rg_scene();
+    sc->device = device;
+    sc->sm_count = prop.multiProcessorCount;
+    auto fail = [&](int code) { rg_scene_destroy(sc); return code; };
+    if (cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "stream", __FILE__, __LINE__));
+    for (auto &ev : sc->ev)
+        if (cudaEventCreate(&ev) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__));
+    if (cudaMalloc(&sc->d_counters, sizeof(DCounters)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "counters", __FILE__, __LINE__));
+    if (cudaMallocHost(&sc->h_counters, sizeof(DCounters)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "counters", __FILE__, __LINE__));
+    rc = build_scene(sc, desc);
+    if (rc) return fail(rc);
+    *out = sc;
+    return RG_OK;
+}
+
+int rg_scene_set_option(rg_scene *sc, int32_t key, int64_t value) {
+    if (!sc) { set_error("scene is NULL"); return RG_E_INVALID; }
+    switch (key) {
+        case RG_OPT_PIPELINE:
+            if (value != RG_PIPELINE_WAVEFRONT && value != RG_PIPELINE_MEGAKERNEL) break;
+            sc->pipeline = (int)value;
+            return RG_OK;
+        case RG_OPT_ACCEL:
+            if (value < RG_ACCEL_AUTO || value > RG_ACCEL_GRID) break;
+            sc->accel = (int)value;
+            return RG_OK;
+        case RG_OPT_MAX_DEPTH:   // main.rs:119-123: a limit only lowers the scene's own depth
+            if (value < 0) break;
+            sc->ds.max_depth = (uint64_t)value < sc->scene_max_depth ? (uint32_t)value : sc->scene_max_depth;
+            return RG_OK;
+        case RG_OPT_BATCH_PIXELS:
+            if (value < 0) break;
+            sc->batch_pixels = (uint64_t)value;
+            return RG_OK;
+        case RG_OPT_VERIFY_CULL:
+            sc->verify_cull = value != 0;
+            return RG_OK;
+        default: break;
+    }
+    set_error("bad option key %d / value %lld", key, (long long)value);
+    return RG_E_INVALID;
+}
+
+static int check_dims(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1) {
+    if (!sc) { set_error("scene is NULL"); return RG_E_INVALID; }
+    if (w == 0 || h == 0) { set_error("empty image %ux%u", w, h); return RG_E_INVALID; }
+    if (w < h) { set_error("width %u < height %u: portrait images are not supported (ray.rs:42)", w, h); return RG_E_PORTRAIT; }
+    if ((uint64_t)w * h > 0xFFFFFFFFull) { set_error("width*height overflows u32 (rendering.rs:27)"); return RG_E_TOO_LARGE; }
+    if (y0 > y1 || y1 > h) { set_error("bad row range [%u, %u) of %u", y0, y1, h); return RG_E_INVALID; }
+    return RG_OK;
+}
+
+static int mega_render(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, uchar4 *d_out,
+                       cudaStream_t stream, rg_stats *st) {
+    const uint64_t npix = (uint64_t)(y1 - y0) * w;
+    RG_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(DCounters), stream));
+    RG_CUDA(cudaEventRecord(sc->ev[0], stream));
+    if (npix) {
+        const unsigned blocks = (unsigned)((npix + 127) / 128);
+        if (sc->ds.max_depth <= 12) k_render_mega<12><<<blocks, 128, 0, stream>>>(sc->ds, w, h, y0, y1, d_out, sc->d_counters);
+        else k_render_mega<RG_MAX_DEPTH><<<blocks, 128, 0, stream>>>(sc->ds, w, h, y0, y1, d_out, sc->d_counters);
+        RG_CUDA(cudaGetLastError());
+    }
+    RG_CUDA(cudaEventRecord(sc->ev[1], stream));
+    RG_CUDA(cudaMemcpyAsync(sc->h_counters, sc->d_counters, sizeof(DCounters), cudaMemcpyDeviceToHost, stream));
+    RG_CUDA(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    RG_CUDA(cudaEventElapsedTime(&ms, sc->ev[0], sc->ev[1]));
+    const DCounters &c = *sc->h_counters;
+    st->rays_primary = c.rays[0];
+    st->rays_shadow = c.rays[1];
+    st->rays_reflection = c.rays[2];
+    st->rays_transmission = c.rays[3];
+    st->err_nan_distance = c.err_nan;
+    st->err_transmission_none = c.err_trans;
+    st->err_aabb_normal = c.err_aabb;
+    st->ms_device = ms;
+    st->ms_trace = ms;
+    st->gpu_launches = npix ? 1 : 0;
+    st->batches = 1;
+    st->accel_used = RG_ACCEL_BRUTE;
+    uint64_t rays = c.rays[0] + c.rays[1] + c.rays[2] + c.rays[3];
+    st->body_tests = rays * sc->n_bodies;
+    st->exact_tests = st->body_tests;
+    return RG_OK;
+}
+
+int rg_render_rows_device(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, void *d_rgba_out,
+                          void *cuda_stream, rg_stats *stats) {
+    int rc = check_dims(sc, w, h, y0, y1);
+    if (rc) return rc;
+    if (!d_rgba_out && y1 > y0) { set_error("output pointer is NULL"); return RG_E_INVALID; }
+    auto t0 = std::chrono::steady_clock::now();
+    RG_CUDA(cudaSetDevice(sc->device));
+    rg_stats local;
+    std::memset(&local, 0, sizeof(local));
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    if (sc->pipeline == RG_PIPELINE_MEGAKERNEL) rc = mega_render(sc, w, h, y0, y1, (uchar4 *)d_rgba_out, stream, &local);
+    else rc = wavefront_render(sc, w, h, y0, y1, (uchar4 *)d_rgba_out, stream, &local);
+    local.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (stats) *stats = local;
+    return rc;
+}
+
+int rg_render_rows(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, uint8_t *rgba_out, rg_stats *stats) {
+    int rc = check_dims(sc, w, h, y0, y1);
+    if (rc) return rc;
+    if (!rgba_out && y1 > y0) { set_error("output pointer is NULL"); return RG_E_INVALID; }
+    auto t0 = std::chrono::steady_clock::now();
+    RG_CUDA(cudaSetDevice(sc->device));
+    const size_t bytes = (size_t)(y1 - y0) * w * 4;
+    if ((rc = sc->frame.reserve(bytes ? bytes : 4))) return rc;
+    rg_stats local;
+    std::memset(&local, 0, sizeof(local));
+    rc = rg_render_rows_device(sc, w, h, y0, y1, sc->frame.ptr, sc->stream, &local);
+    if (rc) return rc;
+    if (bytes) {
+        RG_CUDA(cudaMemcpyAsync(rgba_out, sc->frame.ptr, bytes, cudaMemcpyDeviceToHost, sc->stream));
+        RG_CUDA(cudaStreamSynchronize(sc->stream));
+    }
+    local.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (stats) *stats = local;
+    return RG_OK;
+}
+
+int rg_render(rg_scene *sc, uint32_t w, uint32_t h, uint8_t *rgba_out, rg_stats *stats) {
+    return rg_render_rows(sc, w, h, 0, h, rgba_out, stats);
+}
+
+static void accumulate(rg_stats *total, const rg_stats &s) {
+    total->rays_primary += s.rays_primary;
+    total->rays_shadow += s.rays_shadow;
+    total->rays_reflection += s.rays_reflection;
+    total->rays_transmission += s.rays_transmission;
+    total->body_tests += s.body_tests;
+    total->exact_tests += s.exact_tests;
+    total->cull_unsound += s.cull_unsound;
+    total->err_nan_distance += s.err_nan_distance;
+    total->err_transmission_none += s.err_transmission_none;
+    total->err_aabb_normal += s.err_aabb_normal;
+    total->ms_device += s.ms_device;
+    total->ms_trace += s.ms_trace;
+    total->gpu_launches += s.gpu_launches;
+    total->batches += s.batches;
+    if (s.max_level > total->max_level) total->max_level = s.max_level;
+    total->accel_used = s.accel_used;
+}
+
+int rg_render_stream(rg_scene *sc, uint32_t w, uint32_t h, uint32_t band_rows, rg_rows_cb cb, void *user, rg_stats *stats) {
+    int rc = check_dims(sc, w, h, 0, h);
+    if (rc) return rc;
+    if (!cb) { set_error("callback is NULL"); return RG_E_INVALID; }
+    auto t0 = std::chrono::steady_clock::now();
+    RG_CUDA(cudaSetDevice(sc->device));
+    if (band_rows == 0) {
+        uint64_t rows = (1ull << 20) / w;   // ~1 Mpixel per band
+        band_rows = (uint32_t)(rows < 1 ? 1 : rows);
+    }
+    if (band_rows > h) band_rows = h;
+    const size_t band_bytes = (size_t)band_rows * w * 4;
+    if (sc->h_frame_cap < band_bytes) {
+        if (sc->h_frame) cudaFreeHost(sc->h_frame);
+        sc->h_frame = nullptr;
+        sc->h_frame_cap = 0;
+        RG_CUDA(cudaMallocHost(&sc->h_frame, band_bytes));
+        sc->h_frame_cap = band_bytes;
+    }
+    rg_stats total;
+    std::memset(&total, 0, sizeof(total));
+    for (uint32_t y0 = 0; y0 < h; y0 += band_rows) {
+        uint32_t y1 = y0 + band_rows < h ? y0 + band_rows : h;
+        rg_stats s;
+        rc = rg_render_rows(sc, w, h, y0, y1, sc->h_frame, &s);
+        if (rc) return rc;
+        accumulate(&total, s);
+        if (cb(y0, y1 - y0, w, sc->h_frame, user) != 0) {   // closed channel: rendering.rs:53-54,67
+            set_error("render cancelled by the row callback at row %u", y0);
+            total.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (stats) *stats = total;
+            return RG_E_CANCELLED;
+        }
+    }
+    total.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (stats) *stats = total;
+    return RG_OK;
+}
+
+int rg_measure_peaks(int32_t device, double *fp32_tflops, double *fp64_tflops, double *sm_clock_mhz) {
+    int ndev = rg_device_count();
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return ndev ? RG_E_INVALID : RG_E_CUDA; }
+    RG_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    RG_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    void *out = nullptr;
+    long long *cyc = nullptr;
+    RG_CUDA(cudaMalloc(&out, 64));
+    RG_CUDA(cudaMalloc(&cyc, sizeof(long long)));
+    cudaEvent_t e0, e1;
+    RG_CUDA(cudaEventCreate(&e0));
+    RG_CUDA(cudaEventCreate(&e1));
+    double best32 = 0, best64 = 0, mhz = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        const int it32 = 1 << 16, it64 = 1 << 14;
+        float ms = 0;
+        RG_CUDA(cudaEventRecord(e0));
+        k_fma_peak<float><<<blocks, threads>>>((float *)out, it32, 1.0000001f, 1e-9f, cyc);
+        RG_CUDA(cudaEventRecord(e1));
+        RG_CUDA(cudaEventSynchronize(e1));
+        RG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = (double)blocks * threads * it32 * 8.0 * 2.0 / (ms * 1e-3) / 1e12;
+        if (rep && tf > best32) {
+            best32 = tf;
+            long long c = 0;
+            RG_CUDA(cudaMemcpy(&c, cyc, sizeof(c), cudaMemcpyDeviceToHost));
+            // the sampled block runs for the kernel's whole life only approximately; a clock estimate
+            mhz = (double)c / (ms * 1e-3) / 1e6;
+        }
+        RG_CUDA(cudaEventRecord(e0));
+        k_fma_peak<double><<<blocks, threads>>>((double *)out, it64, 1.0000001, 1e-9, nullptr);
+        RG_CUDA(cudaEventRecord(e1));
+        RG_CUDA(cudaEventSynchronize(e1));
+        RG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        tf = (double)blocks * threads * it64 * 8.0 * 2.0 / (ms * 1e-3) / 1e12;
+        if (rep && tf > best64) best64 = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    cudaFree(cyc);
+    if (fp32_tflops) *fp32_tflops = best32;
+    if (fp64_tflops) *fp64_tflops = best64;
+    if (sm_clock_mhz) *sm_clock_mhz = mhz;
+    return RG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// rg_host.h — host-side state behind the opaque `rg_scene` handle.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "rg_scene.cuh"
+
+namespace rg {
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define RG_CUDA(call)                                                      \
+    do {                                                                   \
+        cudaError_t _e = (call);                                           \
+        if (_e != cudaSuccess) return rg::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// A device allocation that only ever grows; kept across frames so that a steady-state
+// render performs no cudaMalloc.
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <typename T> T *as() const { return reinterpret_cast<T *>(ptr); }
+};
+
+// Scratch of the wavefront pipeline (rg_wavefront.cu).
+struct WavefrontScratch {
+    DeviceBuffer ray[2];        // ping-pong path-ray queues: 3 x double2 per ray
+    DeviceBuffer hit_t, hit_body;
+    DeviceBuffer sray;          // shadow-ray queue: 3 x double2 per ray
+    DeviceBuffer s_tmax;        // light.distance(hit_point) per shadow ray
+    DeviceBuffer s_ab;          // (max(n.L,0), intensity) per shadow ray
+    DeviceBuffer s_lit;         // in_light byte per shadow ray
+    DeviceBuffer lit_bc;        // float4 (body colour, albedo) per lit hit
+    DeviceBuffer lit_node;      // node index per lit hit
+    std::vector<DeviceBuffer> nodes;   // per level: NodeA float4 + NodeB uint4
+    void release();
+};
+
+}  // namespace rg
+
+struct rg_scene {
+    int device = 0;
+    rg::DScene ds{};                    // device pointers inside
+    std::vector<void *> owned;          // cudaMalloc'd scene arrays
+    std::vector<cudaArray_t> tex_arrays;
+    std::vector<cudaTextureObject_t> tex_objs;
+    rg::DCounters *d_counters = nullptr;
+    rg::DCounters *h_counters = nullptr;   // pinned
+    cudaStream_t stream = nullptr;         // library-owned stream for host-buffer renders
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    rg::DeviceBuffer frame;                // RGBA8 staging for host-buffer renders
+    uint8_t *h_frame = nullptr;            // pinned staging
+    size_t h_frame_cap = 0;
+    rg::WavefrontScratch wf;
+    // options
+    int pipeline = RG_PIPELINE_WAVEFRONT;
+    int accel = RG_ACCEL_AUTO;
+    uint32_t scene_max_depth = 0;          // as given in the desc
+    uint64_t batch_pixels = 0;
+    int verify_cull = 0;
+    // derived
+    uint32_t n_bodies = 0;
+    int sm_count = 0;
+};
+
+namespace rg {
+// rg_wavefront.cu
+int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0, uint32_t y1,
+                     uchar4 *d_out, cudaStream_t stream, rg_stats *st);
+// rg_grid.cu
+int grid_build(rg_scene *sc, const std::vector<double> &sph /* n x 4 */);
+}  // namespace rg
