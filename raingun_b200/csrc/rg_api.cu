@@ -202,7 +202,9 @@ static int build_scene(rg_scene *sc, const rg_scene_desc *d) {
         have = true;
     }
     for (int k = 0; k < 3; ++k) ds.cull_ref[k] = have ? 0.5 * (lo[k] + hi[k]) : 0.0;
-    std::vector<float4> cull(ds.n_spheres);
+    // padded to a multiple of kCullPad records that reject everything (K = +inf)
+    const size_t cull_padded = ((size_t)ds.n_spheres + 3) / 4 * 4;
+    std::vector<float4> cull(cull_padded, make_float4(0.f, 0.f, 0.f, std::numeric_limits<float>::infinity()));
     for (uint32_t i = 0; i < ds.n_spheres; ++i) {
         double cx = sph[4 * (size_t)i] - ds.cull_ref[0], cy = sph[4 * (size_t)i + 1] - ds.cull_ref[1],
                cz = sph[4 * (size_t)i + 2] - ds.cull_ref[2], r = sph[4 * (size_t)i + 3];
@@ -244,7 +246,7 @@ static int build_scene(rg_scene *sc, const rg_scene_desc *d) {
     if ((rc = upload(sc, cull.data(), cull.size(), &ds.cull4))) return rc;
     if ((rc = upload(sc, misc_body.data(), misc_body.size(), &ds.misc_body))) return rc;
     if ((rc = create_textures(sc, d))) return rc;
-    if ((rc = grid_build(sc, sph))) return rc;
+    if ((rc = grid_build(sc, sph, cull))) return rc;
     return RG_OK;
 }
 
@@ -353,7 +355,7 @@ int rg_scene_set_option(rg_scene *sc, int32_t key, int64_t value) {
             sc->batch_pixels = (uint64_t)value;
             return RG_OK;
         case RG_OPT_VERIFY_CULL:
-            sc->verify_cull = value != 0;
+            sc->verify_cull = (int)value;
             return RG_OK;
         default: break;
     }

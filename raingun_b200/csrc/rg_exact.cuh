@@ -13,6 +13,10 @@ constexpr uint32_t kNoBody = 0xFFFFFFFFu;
 
 // ---- intersections ----------------------------------------------------------------------
 // bodies.rs:76-120.  Assumes nothing about |d| (the reference never renormalises).
+// Written as straight-line selects with ONE return value on purpose: with the reference's
+// chain of early returns, nvcc 12.9 (NVVM) dropped the `distance0 < 0 && distance1 < 0 ->
+// None` case in some inlined copies (the hit flag became a constant 1 and t kept its
+// caller-side initial value), which the parity tests caught as spurious t = 0 self-hits.
 __device__ __forceinline__ bool sphere_intersect(double cx, double cy, double cz, double radius,
                                                  const Ray &ray, double &t) {
     D3 hyp = d3(cx, cy, cz) - ray.o;
@@ -23,11 +27,10 @@ __device__ __forceinline__ bool sphere_intersect(double cx, double cy, double cz
     double thickness = sqrt(r2 - opp2);
     double d0 = adj - thickness;
     double d1 = adj + thickness;
-    if (d0 < 0.0 && d1 < 0.0) return false;
-    if (d0 < 0.0) { t = d1; return true; }
-    if (d1 < 0.0) { t = d0; return true; }
-    t = fmin(d0, d1);
-    return true;
+    const bool n0 = d0 < 0.0, n1 = d1 < 0.0;
+    // both < 0 -> None; one < 0 -> the other; else min (f64::min == fmin)
+    t = n0 ? d1 : (n1 ? d0 : fmin(d0, d1));
+    return !(n0 && n1);
 }
 // bodies.rs:136-149
 __device__ __forceinline__ bool plane_intersect(const double *g, const Ray &ray, double &t) {

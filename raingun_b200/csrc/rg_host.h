@@ -76,5 +76,5 @@ namespace rg {
 int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0, uint32_t y1,
                      uchar4 *d_out, cudaStream_t stream, rg_stats *st);
 // rg_grid.cu
-int grid_build(rg_scene *sc, const std::vector<double> &sph /* n x 4 */);
+int grid_build(rg_scene *sc, const std::vector<double> &sph /* n x 4 */, const std::vector<float4> &cull);
 }  // namespace rg

@@ -51,7 +51,8 @@ struct GridDev {            // see rg_grid.cuh
     float cell[3];
     int32_t dim[3];
     const uint32_t *cell_start;   // [ncells + 1]
-    const uint32_t *cell_items;   // sphere indices (into the sphere list)
+    const uint32_t *cell_items;   // sphere indices (into the sphere list), cell by cell
+    const float4 *cell_cull4;     // the same spheres' FP32 cull records, in the same order
     uint32_t n_loose;             // spheres kept out of the grid (too large): brute-forced
     const uint32_t *loose;        // their sphere-list indices
     uint32_t enabled;

@@ -1,0 +1,304 @@
+// rg_trace.cuh — Scene::trace (scene.rs:34-39) for a queue of rays: the hot loop.
+//
+// k_trace_brute is the reference algorithm — every ray against every body — arranged for
+// the B200:
+//   * the sphere list is streamed through shared memory in chunks by 1-D bulk async copies
+//     (cp.async.bulk + mbarrier, double-buffered), one 16-byte FP32 cull record per sphere;
+//   * each thread owns R rays (register-tiled), so one broadcast LDS.128 feeds 32*R tests;
+//   * a test is 7 FFMA + 1 FSETP (rg_cull.h): a CONSERVATIVE reject in FP32;
+//   * the rare survivors are not evaluated in the divergent inner loop: they are appended
+//     to a per-warp candidate queue with __ballot_sync/__popc and evaluated 32 at a time,
+//     one candidate per lane, with the reference's exact FP64 test (rg_exact.cuh);
+//   * the per-ray result is the lexicographic min of (distance, original body index), the
+//     order-independent form of min_by's first-minimum rule.
+// ANY = true is the shadow-ray variant: shade_diffuse only asks whether the nearest hit is
+// farther than the light (rendering.rs:150-155), which is false exactly when SOME body is
+// hit at t <= light.distance; so any such hit decides and no minimum is needed.
+#pragma once
+#include <cstdio>
+#include "rg_cull.h"
+#include "rg_exact.cuh"
+
+namespace rg {
+
+constexpr int kTraceThreads = 256;
+constexpr int kTraceWarps = kTraceThreads / 32;
+constexpr int kChunkSpheres = 1024;                 // 16 KB per stage
+constexpr int kCullPad = 4;                         // cull4[] is padded to a multiple of this
+constexpr int kSlotBits = 10;                       // local ray slot: r * 256 + tid  (R <= 4)
+
+struct RayQueue {            // 3 x double2 per ray: (ox,oy) (oz,dx) (dy,dz) — 128-bit coalesced traffic
+    double2 *a, *b, *c;
+};
+
+struct TraceArgs {
+    RayQueue q;
+    const double *tmax;      // ANY: light.distance(hit_point) per ray
+    uint32_t n;
+    double *out_t;           // nearest: distance (undefined when body == kNoBody)
+    uint32_t *out_body;      // nearest: original body index or kNoBody
+    uint8_t *out_lit;        // ANY: 1 = in light
+    DCounters *ctr;
+    int verify;              // RG_OPT_VERIFY_CULL
+};
+
+__device__ __forceinline__ Ray load_ray(const RayQueue &q, uint32_t i) {
+    double2 a = q.a[i], b = q.b[i], c = q.c[i];
+    Ray r;
+    r.o = d3(a.x, a.y, b.x);
+    r.d = d3(b.y, c.x, c.y);
+    return r;
+}
+__device__ __forceinline__ void store_ray(const RayQueue &q, uint32_t i, const Ray &r) {
+    q.a[i] = make_double2(r.o.x, r.o.y);
+    q.b[i] = make_double2(r.o.z, r.d.x);
+    q.c[i] = make_double2(r.d.y, r.d.z);
+}
+
+// ---- mbarrier / bulk-copy primitives (sm_90+ PTX; SASS: SYNCS.*, UBLKCP) ------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Per-ray constants of the FP32 cull (rg_cull.h), derived once from the FP64 ray.
+struct CullRay {
+    float dx, dy, dz, nod;      // d, -(o'.d)
+    float o2x, o2y, o2z, thr;   // -2 o', -|o'|^2 + m_r   (thr = +inf: never reject)
+};
+__device__ __forceinline__ CullRay make_cull_ray(const DScene &s, const Ray &ray, bool active) {
+    CullRay c;
+    D3 op = ray.o - d3(s.cull_ref[0], s.cull_ref[1], s.cull_ref[2]);
+    double O2 = dot(op, op), D2 = dot(ray.d, ray.d), od = dot(op, ray.d);
+    bool cullable = fabs(D2 - 1.0) <= kCullUnitTol && O2 < kCullHuge;    // false on NaN
+    c.dx = (float)ray.d.x; c.dy = (float)ray.d.y; c.dz = (float)ray.d.z;
+    c.nod = (float)(-od);
+    c.o2x = (float)(-2.0 * op.x); c.o2y = (float)(-2.0 * op.y); c.o2z = (float)(-2.0 * op.z);
+    c.thr = cullable ? (float)(-O2 + kCullU * kCullRayO2 * O2) : __int_as_float(0x7f800000);
+    if (!active) {   // a lane without a ray rejects everything it can
+        c.dx = c.dy = c.dz = c.nod = c.o2x = c.o2y = c.o2z = 0.0f;
+        c.thr = __int_as_float(0xff800000);
+    }
+    return c;
+}
+// true = the sphere is certainly missed (the reference's `opp2 > r2` holds); false = must be
+// tested exactly.  NaN anywhere compares false, i.e. "test exactly".
+__device__ __forceinline__ bool cull_reject(const CullRay &c, float4 sp) {
+    float s = fmaf(sp.x, c.dx, fmaf(sp.y, c.dy, fmaf(sp.z, c.dz, c.nod)));
+    float q = fmaf(sp.x, c.o2x, fmaf(sp.y, c.o2y, fmaf(sp.z, c.o2z, sp.w)));
+    float g = fmaf(-s, s, q);
+    return g > c.thr;
+}
+
+template <bool ANY, int R>
+__global__ void __launch_bounds__(kTraceThreads, (R >= 4 ? 2 : 3))
+k_trace_brute(const DScene s, const TraceArgs a) {
+    static_assert(R * kTraceThreads <= (1 << kSlotBits), "slot bits");
+    __shared__ __align__(128) float4 stage[2][kChunkSpheres];
+    __shared__ uint64_t mbar[2];
+    __shared__ uint32_t cq[kTraceWarps][64];
+    __shared__ double best_t[R * kTraceThreads];
+    __shared__ uint32_t best_b[R * kTraceThreads];   // nearest: body; ANY: 1 = occluded
+    __shared__ uint8_t tag[R * kTraceThreads];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t block_base = blockIdx.x * (uint32_t)(R * kTraceThreads);
+    const uint32_t lanemask_lt = (1u << lane) - 1u;
+    const uint32_t nsph = s.n_spheres;
+    const uint32_t nchunks = (nsph + kChunkSpheres - 1) / kChunkSpheres;
+    unsigned long long n_exact = 0;
+    unsigned nan_count = 0, unsound = 0;
+
+    auto chunk_records = [&](uint32_t c) -> uint32_t {
+        uint32_t cnt = nsph - c * kChunkSpheres;
+        if (cnt > (uint32_t)kChunkSpheres) cnt = kChunkSpheres;
+        return (cnt + kCullPad - 1) / kCullPad * kCullPad;
+    };
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0 && nchunks > 0) {
+        uint32_t bytes = chunk_records(0) * 16u;
+        mbar_expect_tx(&mbar[0], bytes);
+        bulk_g2s(&stage[0][0], s.cull4, bytes, &mbar[0]);
+    }
+
+    // ---- prologue: my R rays; the few non-sphere bodies are tested exactly right here
+    CullRay cr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t slot = r * kTraceThreads + tid;
+        const uint32_t i = block_base + slot;
+        const bool active = i < a.n;
+        Ray ray;
+        ray.o = d3(0, 0, 0);
+        ray.d = d3(0, 0, 0);
+        if (active) ray = load_ray(a.q, i);
+        cr[r] = make_cull_ray(s, ray, active);
+        Nearest best;
+        best.init();
+        bool occluded = false;
+        if (active) {
+            const double tmax = ANY ? a.tmax[i] : 0.0;
+            for (uint32_t m = 0; m < s.n_misc; ++m) {
+                uint32_t b = s.misc_body[m];
+                double t;
+                if (misc_intersect(s, b, ray, t)) {
+                    if (t != t) { ++nan_count; continue; }
+                    if (ANY) occluded = occluded || (t <= tmax);
+                    else best.offer(t, b);
+                }
+            }
+            n_exact += s.n_misc;
+        }
+        best_t[slot] = best.t;
+        best_b[slot] = ANY ? (occluded ? 1u : 0u) : best.body;
+    }
+    uint32_t qn = 0;   // warp-uniform: candidates waiting in cq[warp]
+
+    // Evaluates candidates cq[warp][first .. first+count) — one per lane — exactly.
+    auto drain = [&](uint32_t first, uint32_t count) {
+        bool have = (uint32_t)lane < count;
+        uint32_t slot = 0, sph = 0;
+        bool hit = false;
+        double t = 0.0;
+        if (have) {
+            uint32_t e = cq[warp][first + lane];
+            slot = e & ((1u << kSlotBits) - 1u);
+            sph = e >> kSlotBits;
+            Ray ray = load_ray(a.q, block_base + slot);
+            double4 sp = s.sph[sph];
+            hit = sphere_intersect(sp.x, sp.y, sp.z, sp.w, ray, t);
+            ++n_exact;
+            if (hit && t != t) { ++nan_count; hit = false; }
+#ifdef RG_DEBUG_DRAIN
+            if (hit && t == 0.0) printf("drain: ray %u slot %u sph %u o=(%.17g,%.17g,%.17g) d=(%.17g,%.17g,%.17g) sp=(%.17g,%.17g,%.17g,%.17g)\n", block_base + slot, slot, sph, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, sp.x, sp.y, sp.z, sp.w);
+#endif
+        }
+        if (ANY) {
+            if (hit && t <= a.tmax[block_base + slot]) best_b[slot] = 1u;   // benign race: all write 1
+        } else {
+            const uint32_t body = hit ? s.sph_body[sph] : 0u;
+            bool pend = hit;
+            while (__any_sync(0xffffffffu, pend)) {      // serialise candidates of the same ray
+                if (pend) tag[slot] = (uint8_t)lane;
+                __syncwarp();
+                if (pend && tag[slot] == (uint8_t)lane) {
+                    Nearest cur;
+                    cur.t = best_t[slot];
+                    cur.body = best_b[slot];
+                    cur.offer(t, body);
+                    best_t[slot] = cur.t;
+                    best_b[slot] = cur.body;
+                    pend = false;
+                }
+                __syncwarp();
+            }
+        }
+    };
+
+    // ---- main loop: stream the cull records through shared memory
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const uint32_t st = c & 1u;
+        if (tid == 0 && c + 1 < nchunks) {   // prefetch the next chunk into the other stage
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            uint32_t bytes = chunk_records(c + 1) * 16u;
+            mbar_expect_tx(&mbar[st ^ 1u], bytes);
+            bulk_g2s(&stage[st ^ 1u][0], s.cull4 + (size_t)(c + 1) * kChunkSpheres, bytes, &mbar[st ^ 1u]);
+        }
+        mbar_wait(&mbar[st], (c >> 1) & 1u);
+        const uint32_t cnt = chunk_records(c);
+        const uint32_t sph_base = c * kChunkSpheres;
+        const float4 *sp = stage[st];
+#pragma unroll 1
+        for (uint32_t j = 0; j < cnt; j += 2) {
+            const float4 s0 = sp[j], s1 = sp[j + 1];
+            bool rej[2][R];
+            bool any_pass = a.verify != 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                rej[0][r] = cull_reject(cr[r], s0);
+                rej[1][r] = cull_reject(cr[r], s1);
+                any_pass = any_pass || !rej[0][r] || !rej[1][r];
+            }
+            if (__any_sync(0xffffffffu, any_pass)) {
+                // rare path: find the survivors, queue them (warp ballot / popc compaction)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const uint32_t sph = sph_base + j + u;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const uint32_t slot = r * kTraceThreads + tid;
+                        const bool live = (block_base + slot < a.n) && sph < nsph;
+                        const bool pass = live && !rej[u][r];
+                        if (a.verify && live && rej[u][r]) {   // debug: a culled pair must miss exactly
+                            Ray ray = load_ray(a.q, block_base + slot);
+                            double4 e = s.sph[sph];
+                            double t;
+                            if (sphere_intersect(e.x, e.y, e.z, e.w, ray, t)) ++unsound;
+                        }
+                        const uint32_t mask = __ballot_sync(0xffffffffu, pass);
+                        if (mask) {
+                            if (pass) cq[warp][qn + __popc(mask & lanemask_lt)] = (sph << kSlotBits) | slot;
+                            qn += __popc(mask);
+                            __syncwarp();
+                            if (qn >= 32u) {
+                                drain(qn - 32u, 32u);
+                                qn -= 32u;
+                                __syncwarp();
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();   // everyone is done with stage[st] before it is refilled
+    }
+    if (qn) drain(0u, qn);
+    __syncwarp();
+
+    // ---- epilogue
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t slot = r * kTraceThreads + tid;
+        const uint32_t i = block_base + slot;
+        if (i < a.n) {
+            if (ANY) a.out_lit[i] = best_b[slot] ? 0 : 1;
+            else { a.out_t[i] = best_t[slot]; a.out_body[i] = best_b[slot]; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o);
+        nan_count += __shfl_xor_sync(0xffffffffu, nan_count, o);
+        unsound += __shfl_xor_sync(0xffffffffu, unsound, o);
+    }
+    if (lane == 0) {
+        if (n_exact) atomicAdd(&a.ctr->exact_tests, n_exact);
+        if (nan_count) atomicAdd(&a.ctr->err_nan, (unsigned long long)nan_count);
+        if (unsound) atomicAdd(&a.ctr->cull_unsound, (unsigned long long)unsound);
+    }
+}
+
+}  // namespace rg

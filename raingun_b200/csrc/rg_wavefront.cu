@@ -1,7 +1,453 @@
+// rg_wavefront.cu — the wavefront pipeline: render_image's pixel loop (rendering.rs:24-38)
+// turned inside out.
+//
+// The reference recurses per pixel (get_color <-> cast_ray, rendering.rs:80-130).  Here all
+// rays of one recursion depth form a queue ("level"); per level:
+//     k_trace_*  nearest hit of every path ray           Scene::trace            scene.rs:34-39
+//     k_shade    hit point, normal, material; emits the level's shadow rays and the next
+//                level's reflection / transmission rays, compacted with warp ballot + popc
+//                                                         get_color, fresnel, Ray::create_*
+//     k_trace_*  (ANY) the shadow rays                    shade_diffuse           rendering.rs:150-155
+//     k_diffuse  the per-light sum, in light order        shade_diffuse           rendering.rs:157-171
+// and after the deepest level, bottom-up:
+//     k_combine  parent colour from its children's        get_color               rendering.rs:88-116
+//     k_quantise Color::rgba                                                      color.rs:32-37
+// Every hit keeps a 32-byte node (colour + child links), so colours are combined in exactly
+// the reference's order and the image is bit-identical to the recursive evaluation —
+// no throughput-weight reformulation, no atomics on pixels.
+#include <algorithm>
+
+#include "rg_grid.cuh"
 #include "rg_host.h"
+#include "rg_trace.cuh"
+
 namespace rg {
-int wavefront_render(rg_scene *, uint32_t, uint32_t, uint32_t, uint32_t, uchar4 *, cudaStream_t, rg_stats *) {
-    set_error("wavefront pipeline not built yet");
-    return RG_E_INVALID;
+
+constexpr uint32_t kChildDefault = 0xFFFFFFFFu;   // child colour is scene.default_color (no node)
+enum : uint32_t { NODE_MISS = 0, NODE_DIFFUSE = 1, NODE_REFLECTING = 2, NODE_REFRACTIVE = 3 };
+
+struct LevelBuffers {
+    RayQueue cur, next, shadow;
+    const double *hit_t;
+    const uint32_t *hit_body;
+    float4 *node_a;        // rgb (final colour after k_combine) + p0 (reflectivity | kr)
+    uint4 *node_b;         // child_reflection, child_transmission, kind, transparency bits
+    double *s_tmax;
+    float2 *s_ab;
+    float4 *lit_bc;
+    uint32_t *lit_node;
+    uint32_t n;
+    uint32_t can_spawn;    // depth + 1 < max_recursion_depth
+};
+
+// rendering.rs:71-72 + ray.rs:37-54: the level-0 queue, one ray per pixel of rows [y0, y1)
+__global__ void __launch_bounds__(256) k_generate(const DScene s, RayQueue q, uint32_t width, uint32_t height,
+                                                  uint32_t y0, uint32_t npix) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const uint32_t y = y0 + i / width, x = i % width;
+    store_ray(q, i, create_prime(s, x, y, width, height));
 }
+
+__global__ void __launch_bounds__(256) k_shade(const DScene s, const LevelBuffers lb, DCounters *ctr) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    const bool active = i < lb.n;
+    bool want_lit = false, want_refl = false, want_trans = false;
+    Ray ray, refl, trans;
+    D3 hp = d3(0, 0, 0), n = d3(0, 0, 0);
+    uint32_t body = kNoBody, kind = NODE_MISS;
+    float4 na = make_float4(s.default_color[0], s.default_color[1], s.default_color[2], 0.0f);
+    float transparency = 0.0f;
+    C3 bc = c3(0, 0, 0);
+    if (active) {
+        body = lb.hit_body[i];
+        if (body != kNoBody) {
+            ray = load_ray(lb.cur, i);
+            hp = ray.o + ray.d * lb.hit_t[i];                       // rendering.rs:81
+            n = surface_normal(s, body, hp, ctr);                  // :83
+            const BodyMat &m = s.mat[body];
+            float u, v;
+            texture_coords(s, body, hp, u, v);
+            bc = body_color(s, body, u, v);
+            if (m.surface == RG_SURFACE_REFRACTIVE) {              // :95-117
+                kind = NODE_REFRACTIVE;
+                float kr = (float)fresnel(ray.d, n, m.p0);
+                na = make_float4(bc.r, bc.g, bc.b, kr);
+                transparency = m.p1;
+                if (kr < 1.0f) {
+                    if (create_transmission(n, ray.d, hp, kShadowBias, m.p0, trans)) want_trans = lb.can_spawn != 0;
+                    else atomicAdd(&ctr->err_trans, 1ull);         // :106 unwrap() on None
+                }
+                refl = create_reflection(n, ray.d, hp);
+                want_refl = lb.can_spawn != 0;
+            } else {
+                want_lit = true;                                   // :87 / :89 shade_diffuse
+                if (m.surface == RG_SURFACE_REFLECTING) {
+                    kind = NODE_REFLECTING;
+                    na.w = m.p0;
+                    refl = create_reflection(n, ray.d, hp);
+                    want_refl = lb.can_spawn != 0;
+                } else {
+                    kind = NODE_DIFFUSE;
+                }
+            }
+        }
+    }
+    // ---- queue compaction: one atomic per warp per queue, slots by ballot + popc
+    const uint32_t m_lit = __ballot_sync(0xffffffffu, want_lit);
+    const uint32_t m_refl = __ballot_sync(0xffffffffu, want_refl);
+    const uint32_t m_trans = __ballot_sync(0xffffffffu, want_trans);
+    uint32_t base_lit = 0, base_next = 0;
+    if (lane == 0) {
+        if (m_lit) base_lit = atomicAdd(&ctr->q_lit, (unsigned)__popc(m_lit));
+        if (m_refl | m_trans) base_next = atomicAdd(&ctr->q_next, (unsigned)(__popc(m_refl) + __popc(m_trans)));
+        if (m_refl) atomicAdd(&ctr->rays[2], (unsigned long long)__popc(m_refl));
+        if (m_trans) atomicAdd(&ctr->rays[3], (unsigned long long)__popc(m_trans));
+    }
+    base_lit = __shfl_sync(0xffffffffu, base_lit, 0);
+    base_next = __shfl_sync(0xffffffffu, base_next, 0);
+    uint32_t child_refl = kChildDefault, child_trans = kChildDefault;
+    if (want_refl) {
+        child_refl = base_next + __popc(m_refl & lt);
+        store_ray(lb.next, child_refl, refl);
+    }
+    if (want_trans) {
+        child_trans = base_next + __popc(m_refl) + __popc(m_trans & lt);
+        store_ray(lb.next, child_trans, trans);
+    }
+    if (want_lit) {
+        // shade_diffuse's per-light setup (rendering.rs:141-149,163): shadow ray from
+        // hit_point + n * SHADOW_BIAS towards the light; the light-dependent scalars are kept
+        // for k_diffuse.
+        const uint32_t j = base_lit + __popc(m_lit & lt);
+        lb.lit_node[j] = i;
+        lb.lit_bc[j] = make_float4(bc.r, bc.g, bc.b, s.mat[body].albedo);
+        Ray sh;
+        sh.o = hp + n * kShadowBias;
+        for (uint32_t l = 0; l < s.n_lights; ++l) {
+            const DLight &L = s.lights[l];
+            sh.d = light_direction_from(L, hp);
+            const uint32_t k = j * s.n_lights + l;
+            store_ray(lb.shadow, k, sh);
+            lb.s_tmax[k] = light_distance(L, hp);
+            lb.s_ab[k] = make_float2(fmaxf((float)dot(n, sh.d), 0.0f), light_intensity(L, hp));
+        }
+    }
+    if (active) {
+        lb.node_a[i] = na;
+        lb.node_b[i] = make_uint4(child_refl, child_trans, kind, __float_as_uint(transparency));
+    }
 }
+
+// rendering.rs:140,157-171: final_color accumulates light by light, in scene order, then clamps.
+__global__ void __launch_bounds__(256) k_diffuse(const DScene s, const float4 *__restrict__ lit_bc,
+                                                 const uint32_t *__restrict__ lit_node, const float2 *__restrict__ s_ab,
+                                                 const uint8_t *__restrict__ s_lit, float4 *node_a, uint32_t n_lit) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_lit) return;
+    const float4 b = lit_bc[j];
+    const C3 bc = c3(b.x, b.y, b.z);
+    C3 fin = c3(0.0f, 0.0f, 0.0f);
+    for (uint32_t l = 0; l < s.n_lights; ++l) {
+        const uint32_t k = j * s.n_lights + l;
+        const float2 ab = s_ab[k];
+        fin = fin + light_term(bc, s.lights[l], b.w, ab.x, ab.y, s_lit[k] != 0);
+    }
+    fin = clamp01(fin);
+    const uint32_t node = lit_node[j];
+    float4 a = node_a[node];
+    a.x = fin.r; a.y = fin.g; a.z = fin.b;
+    node_a[node] = a;
+}
+
+// get_color's combination of child colours (rendering.rs:88-93, 112-116), one level at a time,
+// deepest level first.  `child_a` is the (already final) level below.
+__global__ void __launch_bounds__(256) k_combine(const DScene s, float4 *node_a, const uint4 *__restrict__ node_b,
+                                                 const float4 *__restrict__ child_a, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 b = node_b[i];
+    if (b.z != NODE_REFLECTING && b.z != NODE_REFRACTIVE) return;
+    const C3 dflt = c3(s.default_color[0], s.default_color[1], s.default_color[2]);
+    float4 a = node_a[i];
+    C3 refl = dflt, refr = dflt;
+    if (b.x != kChildDefault) { float4 c = child_a[b.x]; refl = c3(c.x, c.y, c.z); }
+    if (b.y != kChildDefault) { float4 c = child_a[b.y]; refr = c3(c.x, c.y, c.z); }
+    C3 out;
+    if (b.z == NODE_REFLECTING) {
+        out = (c3(a.x, a.y, a.z) * (1.0f - a.w)) + (refl * a.w);
+    } else {
+        C3 col = (refl * a.w) + (refr * (1.0f - a.w));
+        out = (col * __uint_as_float(b.w)) * c3(a.x, a.y, a.z);
+    }
+    a.x = out.r; a.y = out.g; a.z = out.b;
+    node_a[i] = a;
+}
+
+// Color::rgba (color.rs:32-37): 4 pixels per thread, one 128-bit store
+__global__ void __launch_bounds__(256) k_quantise(const float4 *__restrict__ node_a, uchar4 *out, uint32_t npix) {
+    const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (i4 >= npix) return;
+    if (i4 + 4u <= npix && (reinterpret_cast<uintptr_t>(out + i4) & 15u) == 0) {
+        uchar4 p[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { float4 a = node_a[i4 + k]; p[k] = quantise(c3(a.x, a.y, a.z)); }
+        *reinterpret_cast<uint4 *>(out + i4) = *reinterpret_cast<uint4 *>(p);
+    } else {
+        for (uint32_t k = i4; k < npix && k < i4 + 4u; ++k) { float4 a = node_a[k]; out[k] = quantise(c3(a.x, a.y, a.z)); }
+    }
+}
+
+// RG_OPT_VERIFY_CULL >= 2: re-trace every ray of a queue with the verbatim reference scan and
+// count results that differ from what the production trace kernel wrote (must be 0).
+template <bool ANY>
+__global__ void __launch_bounds__(128) k_verify_trace(const DScene s, const TraceArgs a, int level) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const Ray ray = load_ray(a.q, i);
+    const Nearest h = trace_exact_all(s, ray, a.ctr);
+    bool bad;
+    if (ANY) {
+        const bool lit = !h.found() || h.t > a.tmax[i];
+        bad = (a.out_lit[i] != 0) != lit;
+    } else {
+        bad = a.out_body[i] != h.body || (h.found() && a.out_t[i] != h.t);
+    }
+    if (bad) {
+        unsigned long long k = atomicAdd(&a.ctr->cull_unsound, 1ull);
+        if (k < 8)
+            printf("verify: level %d %s ray %u o=(%.17g,%.17g,%.17g) d=(%.17g,%.17g,%.17g) exact=(%.17g,%u) got=(%.17g,%u)\n", level,
+                   ANY ? "shadow" : "path", i, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, h.t, h.body,
+                   ANY ? (double)a.out_lit[i] : a.out_t[i], ANY ? 0u : a.out_body[i]);
+    }
+}
+
+static RayQueue make_queue(DeviceBuffer &b, size_t cap) {
+    RayQueue q;
+    q.a = b.as<double2>();
+    q.b = q.a + cap;
+    q.c = q.b + cap;
+    return q;
+}
+
+struct EventPool {
+    std::vector<cudaEvent_t> ev;
+    size_t used = 0;
+    cudaEvent_t get() {
+        if (used == ev.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+            ev.push_back(e);
+        }
+        return ev[used++];
+    }
+    ~EventPool() { for (auto e : ev) cudaEventDestroy(e); }
+};
+
+template <bool ANY>
+static int launch_trace(rg_scene *sc, const TraceArgs &ta, bool use_grid, cudaStream_t stream) {
+    if (ta.n == 0) return RG_OK;
+    if (use_grid) {
+        const unsigned blocks = (ta.n + kGridTraceThreads - 1) / kGridTraceThreads;
+        k_trace_grid<ANY><<<blocks, kGridTraceThreads, 0, stream>>>(sc->ds, ta);
+    } else {
+        // register tiling R: 4 rays per thread when there is enough work to fill the chip
+        const uint64_t full = (uint64_t)sc->sm_count * 2 * kTraceThreads;
+        if (ta.n >= full * 4 * 2) {
+            k_trace_brute<ANY, 4><<<(ta.n + 4 * kTraceThreads - 1) / (4 * kTraceThreads), kTraceThreads, 0, stream>>>(sc->ds, ta);
+        } else if (ta.n >= full * 2 * 2) {
+            k_trace_brute<ANY, 2><<<(ta.n + 2 * kTraceThreads - 1) / (2 * kTraceThreads), kTraceThreads, 0, stream>>>(sc->ds, ta);
+        } else {
+            k_trace_brute<ANY, 1><<<(ta.n + kTraceThreads - 1) / kTraceThreads, kTraceThreads, 0, stream>>>(sc->ds, ta);
+        }
+    }
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
+static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0, uint32_t y1, uchar4 *d_out,
+                        cudaStream_t stream, rg_stats *st, bool use_grid, EventPool &events,
+                        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> &trace_spans) {
+    const uint64_t npix64 = (uint64_t)(y1 - y0) * width;
+    if (npix64 == 0) return RG_OK;
+    if (npix64 > 0x7FFFFFFFull) { set_error("batch of %llu pixels is too large", (unsigned long long)npix64); return RG_E_NOMEM; }
+    const uint32_t npix = (uint32_t)npix64;
+    const DScene &ds = sc->ds;
+    const uint32_t L = ds.n_lights;
+    WavefrontScratch &wf = sc->wf;
+    DCounters *dc = sc->d_counters, *hc = sc->h_counters;
+    int rc;
+    auto blocks = [](uint64_t n) { return (unsigned)((n + 255) / 256); };
+
+    std::vector<uint32_t> level_n;
+    uint32_t n = npix, d = 0;
+    if ((rc = wf.ray[0].reserve((size_t)n * 48))) return rc;
+    RayQueue cur = make_queue(wf.ray[0], n);
+    k_generate<<<blocks(n), 256, 0, stream>>>(ds, cur, width, height, y0, npix);
+    RG_CUDA(cudaGetLastError());
+    st->gpu_launches++;
+    st->rays_primary += npix;
+
+    while (n > 0) {
+        const bool can_spawn = d + 1 < ds.max_depth;
+        const uint64_t next_cap = can_spawn ? 2ull * n : 0ull;
+        const uint64_t shadow_cap = (uint64_t)n * L;
+        if (next_cap > 0x7FFFFFFFull || shadow_cap > 0x7FFFFFFFull) {
+            set_error("level %u would hold more than 2^31 rays; use a smaller batch", d);
+            return RG_E_NOMEM;
+        }
+        if (wf.nodes.size() <= d) wf.nodes.resize(d + 1);
+        if ((rc = wf.nodes[d].reserve((size_t)n * 32))) return rc;
+        if ((rc = wf.hit_t.reserve((size_t)n * 8))) return rc;
+        if ((rc = wf.hit_body.reserve((size_t)n * 4))) return rc;
+        DeviceBuffer &nextbuf = wf.ray[(d + 1) & 1];
+        if ((rc = nextbuf.reserve((size_t)std::max<uint64_t>(next_cap, 1) * 48))) return rc;
+        if ((rc = wf.sray.reserve((size_t)std::max<uint64_t>(shadow_cap, 1) * 48))) return rc;
+        if ((rc = wf.s_tmax.reserve((size_t)std::max<uint64_t>(shadow_cap, 1) * 8))) return rc;
+        if ((rc = wf.s_ab.reserve((size_t)std::max<uint64_t>(shadow_cap, 1) * 8))) return rc;
+        if ((rc = wf.s_lit.reserve((size_t)std::max<uint64_t>(shadow_cap, 1)))) return rc;
+        if ((rc = wf.lit_bc.reserve((size_t)n * 16))) return rc;
+        if ((rc = wf.lit_node.reserve((size_t)n * 4))) return rc;
+
+        // nearest hits of this level
+        TraceArgs ta{};
+        ta.q = cur;
+        ta.n = n;
+        ta.out_t = wf.hit_t.as<double>();
+        ta.out_body = wf.hit_body.as<uint32_t>();
+        ta.ctr = dc;
+        ta.verify = sc->verify_cull == 1;
+        cudaEvent_t e0 = events.get(), e1 = events.get();
+        RG_CUDA(cudaEventRecord(e0, stream));
+        if ((rc = launch_trace<false>(sc, ta, use_grid, stream))) return rc;
+        RG_CUDA(cudaEventRecord(e1, stream));
+        trace_spans.emplace_back(e0, e1);
+        st->gpu_launches++;
+        if (sc->verify_cull >= 2) k_verify_trace<false><<<(n + 127) / 128, 128, 0, stream>>>(ds, ta, (int)d);
+
+        LevelBuffers lb{};
+        lb.cur = cur;
+        lb.next = make_queue(nextbuf, (size_t)std::max<uint64_t>(next_cap, 1));
+        lb.shadow = make_queue(wf.sray, (size_t)std::max<uint64_t>(shadow_cap, 1));
+        lb.hit_t = wf.hit_t.as<double>();
+        lb.hit_body = wf.hit_body.as<uint32_t>();
+        lb.node_a = wf.nodes[d].as<float4>();
+        lb.node_b = reinterpret_cast<uint4 *>(wf.nodes[d].as<float4>() + n);
+        lb.s_tmax = wf.s_tmax.as<double>();
+        lb.s_ab = wf.s_ab.as<float2>();
+        lb.lit_bc = wf.lit_bc.as<float4>();
+        lb.lit_node = wf.lit_node.as<uint32_t>();
+        lb.n = n;
+        lb.can_spawn = can_spawn ? 1u : 0u;
+        RG_CUDA(cudaMemsetAsync(&dc->q_next, 0, 2 * sizeof(unsigned int), stream));
+        k_shade<<<blocks(n), 256, 0, stream>>>(ds, lb, dc);
+        RG_CUDA(cudaGetLastError());
+        st->gpu_launches++;
+        RG_CUDA(cudaMemcpyAsync(&hc->q_next, &dc->q_next, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+        RG_CUDA(cudaStreamSynchronize(stream));
+        const uint32_t n_next = hc->q_next, n_lit = hc->q_lit;
+
+        if (n_lit && L) {
+            TraceArgs sa{};
+            sa.q = lb.shadow;
+            sa.tmax = lb.s_tmax;
+            sa.n = n_lit * L;
+            sa.out_lit = wf.s_lit.as<uint8_t>();
+            sa.ctr = dc;
+            sa.verify = sc->verify_cull == 1;
+            cudaEvent_t s0 = events.get(), s1 = events.get();
+            RG_CUDA(cudaEventRecord(s0, stream));
+            if ((rc = launch_trace<true>(sc, sa, use_grid, stream))) return rc;
+            RG_CUDA(cudaEventRecord(s1, stream));
+            trace_spans.emplace_back(s0, s1);
+            if (sc->verify_cull >= 2) k_verify_trace<true><<<(sa.n + 127) / 128, 128, 0, stream>>>(ds, sa, (int)d);
+            st->gpu_launches++;
+            st->rays_shadow += (uint64_t)n_lit * L;
+        }
+        if (n_lit) {
+            k_diffuse<<<blocks(n_lit), 256, 0, stream>>>(ds, lb.lit_bc, lb.lit_node, lb.s_ab, wf.s_lit.as<uint8_t>(),
+                                                         lb.node_a, n_lit);
+            RG_CUDA(cudaGetLastError());
+            st->gpu_launches++;
+        }
+        level_n.push_back(n);
+        cur = lb.next;
+        n = n_next;
+        ++d;
+    }
+    // bottom-up colour combination, then quantise level 0
+    for (int lvl = (int)level_n.size() - 1; lvl >= 0; --lvl) {
+        const uint32_t ln = level_n[lvl];
+        float4 *a = wf.nodes[lvl].as<float4>();
+        const uint4 *b = reinterpret_cast<const uint4 *>(a + ln);
+        const float4 *child = (size_t)lvl + 1 < level_n.size() ? wf.nodes[lvl + 1].as<float4>() : nullptr;
+        k_combine<<<blocks(ln), 256, 0, stream>>>(ds, a, b, child, ln);
+        RG_CUDA(cudaGetLastError());
+        st->gpu_launches++;
+    }
+    k_quantise<<<blocks(((uint64_t)npix + 3) / 4), 256, 0, stream>>>(wf.nodes[0].as<float4>(), d_out, npix);
+    RG_CUDA(cudaGetLastError());
+    st->gpu_launches++;
+    st->batches++;
+    if (level_n.size() > st->max_level + 1) st->max_level = (uint32_t)level_n.size() - 1;
+    return RG_OK;
+}
+
+int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0, uint32_t y1, uchar4 *d_out,
+                     cudaStream_t stream, rg_stats *st) {
+    const DScene &ds = sc->ds;
+    bool use_grid = false;
+    if (sc->accel == RG_ACCEL_GRID) use_grid = ds.grid.enabled != 0;
+    else if (sc->accel == RG_ACCEL_AUTO) use_grid = ds.grid.enabled != 0 && ds.n_spheres >= 64;
+    st->accel_used = use_grid ? RG_ACCEL_GRID : RG_ACCEL_BRUTE;
+
+    EventPool events;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_spans;
+    RG_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(DCounters), stream));
+    RG_CUDA(cudaEventRecord(sc->ev[0], stream));
+
+    const uint32_t rows = y1 - y0;
+    uint64_t batch_pixels = sc->batch_pixels ? sc->batch_pixels : (16ull << 20);
+    uint32_t batch_rows = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(rows ? rows : 1, batch_pixels / width));
+    uint32_t y = y0;
+    while (y < y1) {
+        uint32_t ye = std::min<uint64_t>((uint64_t)y + batch_rows, y1);
+        rg_stats attempt = *st;
+        int rc = render_batch(sc, width, height, y, ye, d_out + (size_t)(y - y0) * width, stream, &attempt, use_grid,
+                              events, trace_spans);
+        if (rc == RG_E_NOMEM && batch_rows > 1) {   // ray tree larger than memory: retry with half the rows
+            cudaStreamSynchronize(stream);
+            sc->wf.release();
+            batch_rows = (batch_rows + 1) / 2;
+            continue;
+        }
+        if (rc) return rc;
+        *st = attempt;
+        y = ye;
+    }
+    RG_CUDA(cudaEventRecord(sc->ev[1], stream));
+    RG_CUDA(cudaMemcpyAsync(sc->h_counters, sc->d_counters, sizeof(DCounters), cudaMemcpyDeviceToHost, stream));
+    RG_CUDA(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    RG_CUDA(cudaEventElapsedTime(&ms, sc->ev[0], sc->ev[1]));
+    st->ms_device = ms;
+    double tr = 0.0;
+    for (auto &p : trace_spans) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, p.first, p.second) == cudaSuccess) tr += t;
+    }
+    st->ms_trace = tr;
+    const DCounters &c = *sc->h_counters;
+    st->rays_reflection = c.rays[2];
+    st->rays_transmission = c.rays[3];
+    st->exact_tests = c.exact_tests;
+    st->cull_unsound = c.cull_unsound;
+    st->err_nan_distance = c.err_nan;
+    st->err_transmission_none = c.err_trans;
+    st->err_aabb_normal = c.err_aabb;
+    st->body_tests = (st->rays_primary + st->rays_shadow + st->rays_reflection + st->rays_transmission) * (uint64_t)sc->n_bodies;
+    return RG_OK;
+}
+
+}  // namespace rg
