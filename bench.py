@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline benchmark (BASELINE.json: Mrays/s over all bounces and
+ms/frame at 4K, 1/2/4/8 B200, beside the reference's CPU path).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm
+                                                              # (the oracle port; no Rust here)
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...     # N > 1
+
+A step = one full frame of the workload (default C4 = BASELINE.json configs[3]: 3840x2160,
+10,000 mixed reflective/refractive spheres + ground plane, 3 lights, depth 8; synthetic,
+raingun_b200/synth.py).  A ray = one Scene::trace call (rendering.rs:73,126,150).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mrays/sec (all bounces) at 4K; ms/frame in ms_per_step"
+UNIT = "Mrays/s"
+
+
+def flops_per_ray(data) -> float:
+    """F_ray = 17 N_sphere + 16 N_plane + 32 N_disk + 22 N_aabb + 6, every ray
+    charged the full body list (brute-force semantics)."""
+    kinds = np.bincount(np.asarray(data.body_kind, np.int64), minlength=4)
+    return float(17 * kinds[0] + 16 * kinds[1] + 32 * kinds[2] + 22 * kinds[3] + 6)
+
+
+def workload_config(name, spec, data, extra):
+    cfg = {"workload": f"{name}: synthetic {spec.width}x{spec.height}, {spec.spheres} "
+                       f"{'mixed reflecting/refractive/diffuse' if spec.mixed else 'diffuse'} spheres + ground plane, "
+                       f"{spec.lights} lights with shadow rays, depth {spec.depth} (BASELINE.json configs, SURVEY 8d, seed {spec.seed})",
+           "width": spec.width, "height": spec.height, "bodies": int(data.n_bodies), "lights": int(data.n_lights),
+           "max_depth": int(data.max_recursion_depth)}
+    cfg.update(extra)
+    return cfg
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int) -> None:
+        self.proc, self.gpu = None, gpu_index
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2])); power.append(float(p[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "no samples"}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def oracle_sample(data, spec, target_seconds: float, threads=None):
+    """Times the CPU oracle (the restated reference algorithm, all host threads, work-stealing
+    over rows like rayon's par_iter) on a centred row band sized for ~target_seconds."""
+    from oracle import oracle
+    O = oracle()
+    threads = threads or O.hardware_threads()
+    w, h = spec.width, spec.height
+    mid = h // 2
+    probe_rows = max(1, min(h, threads // 4))
+    t0 = time.perf_counter()
+    _, st, _ = O.render_rows(data, w, h, mid, min(h, mid + probe_rows), threads=threads)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    rows = int(max(probe_rows, min(h, target_seconds / dt * probe_rows)))
+    y0 = max(0, mid - rows // 2)
+    y1 = min(h, y0 + rows)
+    return O, threads, y0, y1
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return 0
+    from raingun_b200.examples import bundled_texture_loader
+    from raingun_b200.synth import make_scene
+    data, spec = make_scene(args.workload, texture_loader=bundled_texture_loader)
+    total = max(1, args.steps + args.warmup)
+    per_step = max(1.0, min(15.0, args.reference_budget / total))
+    O, threads, y0, y1 = oracle_sample(data, spec, per_step)
+    w, h = spec.width, spec.height
+    for _ in range(args.warmup):
+        O.render_rows(data, w, h, y0, y1, threads=threads)
+    rays = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, st, _ = O.render_rows(data, w, h, y0, y1, threads=threads)
+        rays += st.rays
+    dt = time.perf_counter() - t0
+    value = rays / dt / 1e6
+    sample = f"rows [{y0},{y1}) of {h} ({y1 - y0} rows x {w} px) per step, all bounces"
+    rays_per_row = rays / max(1, args.steps) / max(1, y1 - y0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / max(1, args.steps) * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.workload, spec, data, {"sample": sample, "parallelism": f"cpu{threads}"}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ms_per_frame_extrapolated": (rays_per_row * h) / (value * 1e6) * 1e3 if value > 0 else None,
+        "note": "reference = CPU restatement of raingun's algorithm (oracle/); cargo/rustc are not in this image",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C4", choices=["C3", "C4", "C5"])
+    ap.add_argument("--accel", default="auto", choices=["auto", "grid", "brute"])
+    ap.add_argument("--schedule", default="steal", choices=["steal", "static"])
+    ap.add_argument("--tile-rows", type=int, default=8)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget (N=1)")
+    ap.add_argument("--reference-budget", type=float, default=150.0, help="--impl reference: total seconds")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch
+    import torch.distributed as dist
+
+    import raingun_b200 as rg
+    from raingun_b200 import _native
+    from raingun_b200.dist import render_frame_sharded
+    from raingun_b200.examples import bundled_texture_loader
+    from raingun_b200.synth import make_scene
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: this benchmark has no CPU fallback"}), flush=True)
+        return 2
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    n_gpus = world
+
+    data, spec = make_scene(args.workload, texture_loader=bundled_texture_loader)
+    w, h = spec.width, spec.height
+    accel = {"auto": rg.ACCEL_AUTO, "grid": rg.ACCEL_GRID, "brute": rg.ACCEL_BRUTE}[args.accel]
+    stream = torch.cuda.current_stream(device)
+    sptr = stream.cuda_stream
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    def reduce_max(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(xs):
+        if world == 1:
+            return [int(x) for x in xs]
+        t = torch.tensor(xs, dtype=torch.int64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [int(x) for x in t.tolist()]
+
+    scene = rg.Scene(data, device=local_rank)
+    scene.set_accel(accel)
+    staging = torch.empty((h * w * 4,), dtype=torch.uint8, device=device)
+    host_frame = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()
+    frame_counter = [0]
+
+    gathered = {}
+
+    def step_resident(sc):
+        """One frame, inputs (scene) and output resident in HBM.  Returns (rays, launches, stats)."""
+        if world == 1:
+            st = sc.render_rows_device(w, h, 0, h, staging.data_ptr(), sptr)
+            return st.rays, st.gpu_launches, st
+        frame_counter[0] += 1
+        res = render_frame_sharded(
+            lambda rows, out: sc.render_rowlist_device(w, h, rows, out.data_ptr(), sptr), w, h, rank, world,
+            frame_counter[0], device, tile_rows=args.tile_rows, schedule=args.schedule, staging=staging)
+        gathered["frame"] = res.frame   # rank 0: the gathered (H, W, 4) frame in HBM
+        return (sum(s.rays for s in res.stats), sum(s.gpu_launches for s in res.stats),
+                res.stats[-1] if res.stats else None)
+
+    # ---- device-resident arm: `value`
+    for _ in range(args.warmup):
+        step_resident(scene)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    rays = launches = 0
+    last_stats = None
+    for _ in range(args.steps):
+        r, l, last_stats = step_resident(scene)
+        rays += r
+        launches += l
+    e1.record(stream)
+    barrier()
+    ms_total = reduce_max(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    rays, launches = reduce_sum([rays, launches])
+    ms_per_step = ms_total / max(1, args.steps)
+    value = rays / (ms_total * 1e-3) / 1e6 if ms_total > 0 else 0.0
+    accel_used = {1: "brute", 2: "grid"}.get(last_stats.accel_used if last_stats else 0, "?")
+
+    # ---- end-to-end arm: every step re-uploads the scene from host arrays through the C ABI
+    # (rg_scene_create = H2D), renders, and reads the RGBA8 frame back into pinned host memory.
+    desc_bytes = int(sum(np.asarray(a).nbytes for a in (
+        data.body_kind, data.body_geom, data.coloration_kind, data.color, data.texture_id, data.texture_offset,
+        data.albedo, data.surface_kind, data.surface_param, data.light_kind, data.light_vec, data.light_color,
+        data.light_intensity)) + sum(t.nbytes for t in data.textures))
+    scene.close()
+
+    def step_e2e():
+        sc = rg.Scene(data, device=local_rank)
+        sc.set_accel(accel)
+        if world == 1:
+            r = sc.render_rows_into(w, h, 0, h, host_frame.data_ptr()).rays
+        else:
+            r, _, _ = step_resident(sc)   # row tiles gathered on rank 0's GPU
+            if rank == 0:
+                host_frame.copy_(gathered["frame"])
+        sc.close()
+        return r
+
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_rays = 0
+    for _ in range(args.steps):
+        e2e_rays += step_e2e()
+    barrier()
+    e2e_s = reduce_max(time.perf_counter() - t0)
+    (e2e_rays,) = reduce_sum([e2e_rays])
+    e2e_value = e2e_rays / e2e_s / 1e6 if e2e_s > 0 else 0.0
+    checksum = int(host_frame.view(-1)[:: 4099].to(torch.int64).sum().item()) if rank == 0 else 0
+
+    # ---- roofline arm (rank 0): the reference algorithm itself — brute force, every ray x every
+    # body — whose dominant kernel k_trace_brute is FP32-pipe bound.
+    roofline = None
+    brute = None
+    if not args.no_roofline:
+        barrier()
+        if rank == 0:
+            fp32_peak, fp64_peak, _ = rg.measure_peaks(local_rank)
+            sc = rg.Scene(data, device=local_rank)
+            sc.set_accel(rg.ACCEL_BRUTE)
+            bsteps = max(1, min(3, args.steps))
+            sc.render_rows_device(w, h, 0, h, staging.data_ptr(), sptr)
+            torch.cuda.synchronize(device)
+            tr_ms = dev_ms = 0.0
+            brays = blaunch = 0
+            for _ in range(bsteps):
+                st = sc.render_rows_device(w, h, 0, h, staging.data_ptr(), sptr)
+                tr_ms += st.ms_trace
+                dev_ms += st.ms_device
+                brays += st.rays
+                blaunch += 2 * (st.max_level + 1)
+            sc.close()
+            fl = flops_per_ray(data)
+            achieved = brays * fl / (tr_ms * 1e-3) / 1e12
+            roofline = {"bound": "fp32", "kernel": "k_trace_brute (nearest + shadow variants), accel=brute",
+                        "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                        "traffic": None,
+                        "algorithmic_flops_per_ray": fl,
+                        "pair_tests_per_s": brays * float(data.n_bodies) / (tr_ms * 1e-3),
+                        "peak_source": "rg_measure_peaks: register-resident FFMA loop on this GPU, this run (MEASURED_PEAKS.json "
+                                       "has no FP32 figure; nominal 74.4 TFLOP/s at 1965 MHz)",
+                        "fp64_peak_tflops": fp64_peak,
+                        "share_of_step": tr_ms / dev_ms if dev_ms > 0 else None}
+            brute = {"value": brays / (dev_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": dev_ms / bsteps,
+                     "ms_trace_kernels": tr_ms / bsteps, "steps": bsteps}
+        barrier()
+
+    # ---- CPU baseline beside it (rank 0, N = 1): the oracle on all host threads, bounded sample
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        O, threads, y0, y1 = oracle_sample(data, spec, args.cpu_seconds)
+        t0 = time.perf_counter()
+        _, ost, _ = O.render_rows(data, w, h, y0, y1, threads=threads)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": ost.rays / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"rows [{y0},{y1}) of {h} ({(y1 - y0) * w} px, {ost.rays} rays) in {dt:.1f} s",
+                        "ms_per_frame_extrapolated": dt * 1e3 * h / max(1, y1 - y0)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.workload, spec, data, {
+                "accel": accel_used, "pipeline": "wavefront",
+                "parallelism": f"row-tiles x{world} ({args.schedule}, {args.tile_rows}-row tiles)" if world > 1 else "1 GPU",
+                "l2": "per-frame working set (ray queues + nodes, several GB) exceeds the 126 MB L2; no explicit flush"}),
+            "rays_per_frame": rays // max(1, args.steps),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": desc_bytes * world,
+                    "d2h_bytes_per_step": h * w * 4, "ms_per_step": e2e_s / max(1, args.steps) * 1e3,
+                    "what": "rg_scene_create (scene H2D) + render + RGBA8 frame D2H into pinned host memory + rg_scene_destroy, per step"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "brute_force": brute,
+            "cpu_baseline": cpu_baseline, "frame_checksum": checksum,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -187,6 +187,14 @@ int rg_render_rows_device(rg_scene *scene, uint32_t width, uint32_t height,
                           uint32_t y0, uint32_t y1, void *d_rgba_out,
                           void *cuda_stream, rg_stats *stats);
 
+/* Row-tile sharding: renders the image rows listed in `rows` (n_rows entries, any order, HOST
+ * array) and writes them compacted, in list order, to DEVICE memory (n_rows*width*4 bytes).
+ * This is the unit a multi-GPU host uses: each GPU renders the row tiles it claimed from a
+ * work-stealing counter, then the tiles are gathered (raingun_b200/dist.py). */
+int rg_render_rowlist_device(rg_scene *scene, uint32_t width, uint32_t height,
+                             const uint32_t *rows, uint32_t n_rows, void *d_rgba_out,
+                             void *cuda_stream, rg_stats *stats);
+
 /* Scene::streaming_render (scene.rs:45-51 -> rendering.rs:40-69): renders in
  * bands of `band_rows` rows (0 = automatic) and hands each finished band to
  * `cb` from the calling thread.  Returns RG_E_CANCELLED if `cb` returned

@@ -125,6 +125,17 @@ class Scene:
         self.last_stats = st
         return st
 
+    def render_rowlist_device(self, width: int, height: int, rows, device_ptr: int, cuda_stream: int = 0) -> Stats:
+        """Row-tile sharding unit: renders the listed image rows, compacted in list order, into
+        HBM at ``device_ptr`` (len(rows)*width*4 bytes)."""
+        rows = np.ascontiguousarray(rows, np.uint32)
+        st = Stats()
+        _native.check(_native.lib().rg_render_rowlist_device(
+            self._h, width, height, ctypes.c_void_p(rows.ctypes.data), int(rows.size), ctypes.c_void_p(device_ptr),
+            ctypes.c_void_p(cuda_stream), ctypes.byref(st)))
+        self.last_stats = st
+        return st
+
     # -- Scene::streaming_render (scene.rs:45-51): finished row bands instead of single pixels
     def streaming_render(self, width: int, height: int, on_rows: Callable[[int, np.ndarray], bool],
                          band_rows: int = 0) -> bool:

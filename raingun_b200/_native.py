@@ -28,7 +28,7 @@ ROWS_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctype
 
 # every symbol include/raingun_b200.h declares
 EXPORTS = ("rg_scene_create", "rg_scene_destroy", "rg_scene_set_option", "rg_render", "rg_render_rows",
-           "rg_render_rows_device", "rg_render_stream", "rg_last_error", "rg_measure_peaks",
+           "rg_render_rows_device", "rg_render_rowlist_device", "rg_render_stream", "rg_last_error", "rg_measure_peaks",
            "rg_device_count")
 
 
@@ -62,6 +62,8 @@ def lib() -> ctypes.CDLL:
     L.rg_render_rows.argtypes = [vp, u32, u32, u32, u32, vp, ctypes.POINTER(Stats)]
     L.rg_render_rows_device.restype = ctypes.c_int
     L.rg_render_rows_device.argtypes = [vp, u32, u32, u32, u32, vp, vp, ctypes.POINTER(Stats)]
+    L.rg_render_rowlist_device.restype = ctypes.c_int
+    L.rg_render_rowlist_device.argtypes = [vp, u32, u32, vp, u32, vp, vp, ctypes.POINTER(Stats)]
     L.rg_render_stream.restype = ctypes.c_int
     L.rg_render_stream.argtypes = [vp, u32, u32, u32, ROWS_CB, vp, ctypes.POINTER(Stats)]
     L.rg_last_error.restype = ctypes.c_char_p

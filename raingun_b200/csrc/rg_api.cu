@@ -6,6 +6,8 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <mutex>
 
 #include "rg_cull.h"
 #include "rg_host.h"
@@ -58,6 +60,13 @@ void WavefrontScratch::release() {
     for (auto &b : nodes) b.release();
     nodes.clear();
 }
+
+// Scratch arenas outlive a scene: destroying a scene parks its (possibly multi-GB) wavefront
+// buffers here and the next scene created on the same device adopts them, so a host that
+// re-uploads the scene every frame does not pay cudaMalloc/cudaFree for them each time.
+struct ParkedScratch { bool used = false; WavefrontScratch wf; DeviceBuffer frame; };
+static std::mutex g_park_mutex;
+static std::map<int, ParkedScratch> g_parked;
 
 template <typename T>
 static int upload(rg_scene *sc, const T *host, size_t count, const T **out) {
@@ -290,8 +299,20 @@ void rg_scene_destroy(rg_scene *sc) {
     for (auto o : sc->tex_objs) cudaDestroyTextureObject(o);
     for (auto a : sc->tex_arrays) cudaFreeArray(a);
     for (auto p : sc->owned) cudaFree(p);
+    {
+        std::lock_guard<std::mutex> lock(g_park_mutex);
+        ParkedScratch &slot = g_parked[sc->device];
+        if (!slot.used) {
+            slot.used = true;
+            slot.wf = std::move(sc->wf);
+            slot.frame = sc->frame;
+            sc->wf = WavefrontScratch{};
+            sc->frame = DeviceBuffer{};
+        }
+    }
     sc->wf.release();
     sc->frame.release();
+    sc->rowlist.release();
     if (sc->h_frame) cudaFreeHost(sc->h_frame);
     if (sc->d_counters) cudaFree(sc->d_counters);
     if (sc->h_counters) cudaFreeHost(sc->h_counters);
@@ -331,6 +352,15 @@ int rg_scene_create(const rg_scene_desc *desc, int32_t device, rg_scene **out) {
     if (cudaMallocHost(&sc->h_counters, sizeof(DCounters)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "counters", __FILE__, __LINE__));
     rc = build_scene(sc, desc);
     if (rc) return fail(rc);
+    {
+        std::lock_guard<std::mutex> lock(g_park_mutex);
+        auto it = g_parked.find(device);
+        if (it != g_parked.end() && it->second.used) {
+            sc->wf = std::move(it->second.wf);
+            sc->frame = it->second.frame;
+            it->second = ParkedScratch{};
+        }
+    }
     *out = sc;
     return RG_OK;
 }
@@ -372,15 +402,15 @@ static int check_dims(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_
     return RG_OK;
 }
 
-static int mega_render(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, uchar4 *d_out,
-                       cudaStream_t stream, rg_stats *st) {
+static int mega_render(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, const uint32_t *d_rows,
+                       uchar4 *d_out, cudaStream_t stream, rg_stats *st) {
     const uint64_t npix = (uint64_t)(y1 - y0) * w;
     RG_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(DCounters), stream));
     RG_CUDA(cudaEventRecord(sc->ev[0], stream));
     if (npix) {
         const unsigned blocks = (unsigned)((npix + 127) / 128);
-        if (sc->ds.max_depth <= 12) k_render_mega<12><<<blocks, 128, 0, stream>>>(sc->ds, w, h, y0, y1, d_out, sc->d_counters);
-        else k_render_mega<RG_MAX_DEPTH><<<blocks, 128, 0, stream>>>(sc->ds, w, h, y0, y1, d_out, sc->d_counters);
+        if (sc->ds.max_depth <= 12) k_render_mega<12><<<blocks, 128, 0, stream>>>(sc->ds, w, h, y0, y1, d_rows, d_out, sc->d_counters);
+        else k_render_mega<RG_MAX_DEPTH><<<blocks, 128, 0, stream>>>(sc->ds, w, h, y0, y1, d_rows, d_out, sc->d_counters);
         RG_CUDA(cudaGetLastError());
     }
     RG_CUDA(cudaEventRecord(sc->ev[1], stream));
@@ -407,21 +437,44 @@ static int mega_render(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32
     return RG_OK;
 }
 
+// Common tail of the device-output entry points: rows [y0, y1), or entries [0, n) of a row list.
+static int render_device(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, const uint32_t *d_rows,
+                         void *d_rgba_out, cudaStream_t stream, rg_stats *stats) {
+    auto t0 = std::chrono::steady_clock::now();
+    rg_stats local;
+    std::memset(&local, 0, sizeof(local));
+    int rc;
+    if (sc->pipeline == RG_PIPELINE_MEGAKERNEL) rc = mega_render(sc, w, h, y0, y1, d_rows, (uchar4 *)d_rgba_out, stream, &local);
+    else rc = wavefront_render(sc, w, h, y0, y1, d_rows, (uchar4 *)d_rgba_out, stream, &local);
+    local.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (stats) *stats = local;
+    return rc;
+}
+
 int rg_render_rows_device(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, void *d_rgba_out,
                           void *cuda_stream, rg_stats *stats) {
     int rc = check_dims(sc, w, h, y0, y1);
     if (rc) return rc;
     if (!d_rgba_out && y1 > y0) { set_error("output pointer is NULL"); return RG_E_INVALID; }
-    auto t0 = std::chrono::steady_clock::now();
     RG_CUDA(cudaSetDevice(sc->device));
-    rg_stats local;
-    std::memset(&local, 0, sizeof(local));
+    return render_device(sc, w, h, y0, y1, nullptr, d_rgba_out, reinterpret_cast<cudaStream_t>(cuda_stream), stats);
+}
+
+int rg_render_rowlist_device(rg_scene *sc, uint32_t w, uint32_t h, const uint32_t *rows, uint32_t n_rows,
+                             void *d_rgba_out, void *cuda_stream, rg_stats *stats) {
+    int rc = check_dims(sc, w, h, 0, h);
+    if (rc) return rc;
+    if (n_rows && (!rows || !d_rgba_out)) { set_error("rows / output pointer is NULL"); return RG_E_INVALID; }
+    for (uint32_t k = 0; k < n_rows; ++k)
+        if (rows[k] >= h) { set_error("rows[%u] = %u is outside the image (height %u)", k, rows[k], h); return RG_E_INVALID; }
+    RG_CUDA(cudaSetDevice(sc->device));
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
-    if (sc->pipeline == RG_PIPELINE_MEGAKERNEL) rc = mega_render(sc, w, h, y0, y1, (uchar4 *)d_rgba_out, stream, &local);
-    else rc = wavefront_render(sc, w, h, y0, y1, (uchar4 *)d_rgba_out, stream, &local);
-    local.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    if (stats) *stats = local;
-    return rc;
+    if (n_rows) {
+        if ((rc = sc->rowlist.reserve((size_t)n_rows * sizeof(uint32_t)))) return rc;
+        RG_CUDA(cudaMemcpyAsync(sc->rowlist.ptr, rows, (size_t)n_rows * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        RG_CUDA(cudaStreamSynchronize(stream));   // `rows` may be pageable and reused by the caller
+    }
+    return render_device(sc, w, h, 0, n_rows, sc->rowlist.as<uint32_t>(), d_rgba_out, stream, stats);
 }
 
 int rg_render_rows(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, uint8_t *rgba_out, rg_stats *stats) {

@@ -57,6 +57,7 @@ struct rg_scene {
     cudaStream_t stream = nullptr;         // library-owned stream for host-buffer renders
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     rg::DeviceBuffer frame;                // RGBA8 staging for host-buffer renders
+    rg::DeviceBuffer rowlist;              // device copy of a caller's row list
     uint8_t *h_frame = nullptr;            // pinned staging
     size_t h_frame_cap = 0;
     rg::WavefrontScratch wf;
@@ -73,8 +74,9 @@ struct rg_scene {
 
 namespace rg {
 // rg_wavefront.cu
+// rows [y0, y1) of the image, or — when d_rows is given — entries [y0, y1) of that row list
 int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0, uint32_t y1,
-                     uchar4 *d_out, cudaStream_t stream, rg_stats *st);
+                     const uint32_t *d_rows, uchar4 *d_out, cudaStream_t stream, rg_stats *st);
 // rg_grid.cu
 int grid_build(rg_scene *sc, const std::vector<double> &sph /* n x 4 */, const std::vector<float4> &cull);
 }  // namespace rg

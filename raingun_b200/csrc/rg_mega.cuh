@@ -41,14 +41,15 @@ __device__ __forceinline__ C3 mega_shade_diffuse(const DScene &s, uint32_t body,
 
 template <int STACK>
 __global__ void __launch_bounds__(128)
-k_render_mega(DScene s, uint32_t width, uint32_t height, uint32_t y0, uint32_t y1, uchar4 *__restrict__ out,
-              DCounters *ctr) {
+k_render_mega(DScene s, uint32_t width, uint32_t height, uint32_t y0, uint32_t y1, const uint32_t *__restrict__ rows,
+              uchar4 *__restrict__ out, DCounters *ctr) {
     const uint64_t npix = (uint64_t)(y1 - y0) * width;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cnt[4] = {0, 0, 0, 0};   // primary, shadow, reflection, transmission
     if (i < npix) {
-        const uint32_t y = y0 + (uint32_t)(i / width);
-        const uint32_t x = (uint32_t)(i - (uint64_t)(y - y0) * width);
+        const uint32_t k = y0 + (uint32_t)(i / width);
+        const uint32_t x = (uint32_t)(i - (uint64_t)(k - y0) * width);
+        const uint32_t y = rows ? rows[k] : k;
         const C3 dflt = c3(s.default_color[0], s.default_color[1], s.default_color[2]);
         MegaFrame stack[STACK];
         int sp = 0;

@@ -41,11 +41,13 @@ struct LevelBuffers {
 };
 
 // rendering.rs:71-72 + ray.rs:37-54: the level-0 queue, one ray per pixel of rows [y0, y1)
+// `rows` (optional) maps the k-th row of the batch to an image row, for row-tile sharding.
 __global__ void __launch_bounds__(256) k_generate(const DScene s, RayQueue q, uint32_t width, uint32_t height,
-                                                  uint32_t y0, uint32_t npix) {
+                                                  uint32_t y0, uint32_t npix, const uint32_t *__restrict__ rows) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
-    const uint32_t y = y0 + i / width, x = i % width;
+    const uint32_t k = y0 + i / width, x = i % width;
+    const uint32_t y = rows ? rows[k] : k;
     store_ray(q, i, create_prime(s, x, y, width, height));
 }
 
@@ -266,8 +268,8 @@ static int launch_trace(rg_scene *sc, const TraceArgs &ta, bool use_grid, cudaSt
     return RG_OK;
 }
 
-static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0, uint32_t y1, uchar4 *d_out,
-                        cudaStream_t stream, rg_stats *st, bool use_grid, EventPool &events,
+static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0, uint32_t y1,
+                        const uint32_t *d_rows, uchar4 *d_out, cudaStream_t stream, rg_stats *st, bool use_grid, EventPool &events,
                         std::vector<std::pair<cudaEvent_t, cudaEvent_t>> &trace_spans) {
     const uint64_t npix64 = (uint64_t)(y1 - y0) * width;
     if (npix64 == 0) return RG_OK;
@@ -284,7 +286,7 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
     uint32_t n = npix, d = 0;
     if ((rc = wf.ray[0].reserve((size_t)n * 48))) return rc;
     RayQueue cur = make_queue(wf.ray[0], n);
-    k_generate<<<blocks(n), 256, 0, stream>>>(ds, cur, width, height, y0, npix);
+    k_generate<<<blocks(n), 256, 0, stream>>>(ds, cur, width, height, y0, npix, d_rows);
     RG_CUDA(cudaGetLastError());
     st->gpu_launches++;
     st->rays_primary += npix;
@@ -394,8 +396,8 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
     return RG_OK;
 }
 
-int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0, uint32_t y1, uchar4 *d_out,
-                     cudaStream_t stream, rg_stats *st) {
+int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0, uint32_t y1,
+                     const uint32_t *d_rows, uchar4 *d_out, cudaStream_t stream, rg_stats *st) {
     const DScene &ds = sc->ds;
     bool use_grid = false;
     if (sc->accel == RG_ACCEL_GRID) use_grid = ds.grid.enabled != 0;
@@ -404,27 +406,31 @@ int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0,
 
     EventPool events;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_spans;
-    RG_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(DCounters), stream));
-    RG_CUDA(cudaEventRecord(sc->ev[0], stream));
-
     const uint32_t rows = y1 - y0;
-    uint64_t batch_pixels = sc->batch_pixels ? sc->batch_pixels : (16ull << 20);
+    const uint64_t batch_pixels = sc->batch_pixels ? sc->batch_pixels : (16ull << 20);
     uint32_t batch_rows = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(rows ? rows : 1, batch_pixels / width));
-    uint32_t y = y0;
-    while (y < y1) {
-        uint32_t ye = std::min<uint64_t>((uint64_t)y + batch_rows, y1);
-        rg_stats attempt = *st;
-        int rc = render_batch(sc, width, height, y, ye, d_out + (size_t)(y - y0) * width, stream, &attempt, use_grid,
+    const rg_stats st0 = *st;
+    for (;;) {   // a ray tree larger than device memory restarts the render with half the rows per batch
+        *st = st0;
+        events.used = 0;
+        trace_spans.clear();
+        RG_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(DCounters), stream));
+        RG_CUDA(cudaEventRecord(sc->ev[0], stream));
+        int rc = RG_OK;
+        for (uint32_t y = y0; y < y1 && rc == RG_OK;) {
+            const uint32_t ye = (uint32_t)std::min<uint64_t>((uint64_t)y + batch_rows, y1);
+            rc = render_batch(sc, width, height, y, ye, d_rows, d_out + (size_t)(y - y0) * width, stream, st, use_grid,
                               events, trace_spans);
-        if (rc == RG_E_NOMEM && batch_rows > 1) {   // ray tree larger than memory: retry with half the rows
+            y = ye;
+        }
+        if (rc == RG_E_NOMEM && batch_rows > 1) {
             cudaStreamSynchronize(stream);
             sc->wf.release();
             batch_rows = (batch_rows + 1) / 2;
             continue;
         }
         if (rc) return rc;
-        *st = attempt;
-        y = ye;
+        break;
     }
     RG_CUDA(cudaEventRecord(sc->ev[1], stream));
     RG_CUDA(cudaMemcpyAsync(sc->h_counters, sc->d_counters, sizeof(DCounters), cudaMemcpyDeviceToHost, stream));

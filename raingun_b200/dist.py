@@ -1,0 +1,165 @@
+"""Row-tile sharding of one frame across the GPUs of a box — the multi-GPU form of
+render_image's ``par_iter`` over pixels (raingun-lib/src/rendering.rs:27-35).
+
+Pixels are independent, so the path shards with NO data-path collective: the scene is
+replicated, the image is cut into tiles of ``tile_rows`` rows, and every rank renders the
+tiles it claims.  Cost per row is very uneven (sky vs sphere field), so tiles are handed out
+by a work-stealing counter — an atomic fetch-add on the c10d store all ranks already share —
+in guided chunks (large first, small last).  The only exchange is the final gather of the
+RGBA8 tiles into rank 0's frame: point-to-point sends over NVLink (NCCL send/recv), i.e.
+rayon's ``collect`` (rendering.rs:34-35).
+
+One process per GPU (torchrun); works unchanged on the gloo backend with CPU tensors, which
+is how the host logic is tested without GPUs (tests/test_dist_gloo.py).
+"""
+from __future__ import annotations
+
+import pickle
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+DEFAULT_TILE_ROWS = 8
+
+
+def n_tiles(height: int, tile_rows: int) -> int:
+    return (height + tile_rows - 1) // tile_rows
+
+
+def tile_rows_range(tile: int, tile_rows: int, height: int) -> range:
+    return range(tile * tile_rows, min(height, (tile + 1) * tile_rows))
+
+
+def rows_of_tiles(tiles: Sequence[int], tile_rows: int, height: int) -> np.ndarray:
+    if len(tiles) == 0:
+        return np.zeros(0, np.uint32)
+    return np.concatenate([np.arange(r.start, r.stop, dtype=np.uint32)
+                           for r in (tile_rows_range(t, tile_rows, height) for t in tiles)])
+
+
+def guided_chunks(num_tiles: int, world: int, min_chunk: int = 1) -> List[List[int]]:
+    """Deterministic guided self-scheduling: each chunk takes ``max(min_chunk, remaining //
+    (2 * world))`` consecutive tiles.  Every rank computes the same list, so a claim is just
+    an index into it."""
+    chunks, start = [], 0
+    while start < num_tiles:
+        size = min(num_tiles - start, max(min_chunk, (num_tiles - start) // (2 * max(world, 1))))
+        chunks.append(list(range(start, start + size)))
+        start += size
+    return chunks
+
+
+def static_chunk(num_tiles: int, world: int, rank: int) -> List[int]:
+    """Interleaved static ownership: tile t belongs to rank t % world."""
+    return list(range(rank, num_tiles, world))
+
+
+class TileCounter:
+    """Work-stealing counter over a c10d store: ``store.add`` is an atomic fetch-add."""
+
+    def __init__(self, store, key: str, chunks: Sequence[Sequence[int]]) -> None:
+        self.store, self.key, self.chunks = store, key, [list(c) for c in chunks]
+
+    def claim(self) -> Optional[List[int]]:
+        idx = int(self.store.add(self.key, 1)) - 1
+        return self.chunks[idx] if idx < len(self.chunks) else None
+
+
+@dataclass
+class ShardResult:
+    frame: Optional[torch.Tensor]          # (H, W, 4) uint8 on rank 0, None elsewhere
+    my_tiles: List[int] = field(default_factory=list)
+    claims: int = 0
+    stats: list = field(default_factory=list)   # whatever render_rowlist returned, per call
+
+
+def default_store():
+    return dist.distributed_c10d._get_default_store()
+
+
+def render_frame_sharded(render_rowlist: Callable[[np.ndarray, torch.Tensor], object], width: int, height: int,
+                         rank: int, world: int, frame_id: int, device: torch.device, store=None,
+                         tile_rows: int = DEFAULT_TILE_ROWS, schedule: str = "steal",
+                         gather: bool = True, staging: Optional[torch.Tensor] = None) -> ShardResult:
+    """Renders one frame across ``world`` ranks.
+
+    ``render_rowlist(rows, out)`` must fill ``out`` (a uint8 tensor of ``len(rows)*width*4``
+    bytes on ``device``) with the listed image rows, compacted in list order — on a GPU that is
+    ``Scene.render_rowlist_device``.  ``schedule`` is ``"steal"`` (work-stealing counter) or
+    ``"static"`` (interleaved ownership, one batch per rank).
+    """
+    nt = n_tiles(height, tile_rows)
+    res = ShardResult(frame=None)
+    row_bytes = width * 4
+    if staging is None:
+        staging = torch.empty((height * row_bytes,), dtype=torch.uint8, device=device)
+    if world == 1:
+        pending = iter([list(range(nt))])
+        claim = lambda: next(pending, None)
+    elif schedule == "steal":
+        if store is None:
+            store = default_store()
+        claim = TileCounter(store, f"raingun/tiles/{frame_id}", guided_chunks(nt, world)).claim
+    elif schedule == "static":
+        pending = iter([static_chunk(nt, world, rank)])
+        claim = lambda: next(pending, None)
+    else:
+        raise ValueError(f"unknown schedule {schedule!r}")
+
+    filled_rows = 0
+    my_rows: List[np.ndarray] = []
+    while True:
+        tiles = claim()
+        if tiles is None:
+            break
+        if not tiles:
+            continue
+        res.claims += 1
+        rows = rows_of_tiles(tiles, tile_rows, height)
+        out = staging[filled_rows * row_bytes:(filled_rows + int(rows.size)) * row_bytes]
+        res.stats.append(render_rowlist(rows, out))
+        res.my_tiles.extend(tiles)
+        my_rows.append(rows)
+        filled_rows += int(rows.size)
+    rows_all = np.concatenate(my_rows) if my_rows else np.zeros(0, np.uint32)
+    if not gather:
+        return res
+
+    # ---- gather: ownership is dynamic, so the row lists travel first (tiny), then the pixels
+    packed = staging[: filled_rows * row_bytes]
+    if world == 1:
+        res.frame = packed.view(height, width, 4) if np.array_equal(rows_all, np.arange(height)) else \
+            _scatter_rows(torch.empty((height, width, 4), dtype=torch.uint8, device=device), rows_all, packed, width)
+        return res
+    if store is None:
+        store = default_store()
+    store.set(f"raingun/rows/{frame_id}/{rank}", pickle.dumps(rows_all))
+    if rank == 0:
+        frame = torch.empty((height, width, 4), dtype=torch.uint8, device=device)
+        _scatter_rows(frame, rows_all, packed, width)
+        lists = {r: pickle.loads(store.get(f"raingun/rows/{frame_id}/{r}")) for r in range(1, world)}
+        recv_bufs, ops = {}, []
+        for r, rl in lists.items():
+            if rl.size:
+                recv_bufs[r] = torch.empty((int(rl.size) * row_bytes,), dtype=torch.uint8, device=device)
+                ops.append(dist.P2POp(dist.irecv, recv_bufs[r], r))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for r, buf in recv_bufs.items():
+            _scatter_rows(frame, lists[r], buf, width)
+        res.frame = frame
+    elif filled_rows:
+        for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, packed, 0)]):
+            req.wait()
+    return res
+
+
+def _scatter_rows(frame: torch.Tensor, rows: np.ndarray, packed: torch.Tensor, width: int) -> torch.Tensor:
+    if rows.size:
+        idx = torch.from_numpy(rows.astype(np.int64)).to(frame.device)
+        frame.index_copy_(0, idx, packed.view(int(rows.size), width, 4))
+    return frame
