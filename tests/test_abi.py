@@ -1,0 +1,83 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/raingun_b200.h
+declares; argument validation that needs no device works; rendering without a device fails
+loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from raingun_b200 import _native
+from raingun_b200.examples import example_scene
+from raingun_b200.scene import SceneDesc, Stats
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "raingun_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rg_[a-z_0-9]+)\s*\(", text)) - {"rg_rows_cb"})
+
+
+def test_header_and_binding_agree():
+    assert declared_functions() == sorted(_native.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _native.lib()
+    for name in declared_functions():
+        assert hasattr(lib, name), name
+
+
+def test_struct_layouts_match_header():
+    # offsets implied by include/raingun_b200.h on LP64
+    assert SceneDesc.fov.offset == 8 and SceneDesc.default_color.offset == 16
+    assert SceneDesc.n_bodies.offset == 28 and SceneDesc.body_kind.offset == 32
+    assert SceneDesc.n_lights.offset == 104 and SceneDesc.light_kind.offset == 112
+    assert SceneDesc.textures.offset == 144 and ctypes.sizeof(SceneDesc) == 152
+    assert ctypes.sizeof(Stats) == 120
+
+
+def test_validation_without_device():
+    lib = _native.lib()
+    out = ctypes.c_void_p()
+    assert lib.rg_scene_create(None, 0, ctypes.byref(out)) == _native.E_INVALID
+    assert b"NULL" in lib.rg_last_error()
+    data = example_scene("test2")
+    data.max_recursion_depth = 65
+    desc, keep = data.to_desc()
+    assert lib.rg_scene_create(ctypes.byref(desc), 0, ctypes.byref(out)) == _native.E_DEPTH
+    data.max_recursion_depth = 10
+    data.body_kind = data.body_kind.copy()
+    data.body_kind[0] = 9
+    desc, keep = data.to_desc()
+    assert lib.rg_scene_create(ctypes.byref(desc), 0, ctypes.byref(out)) == _native.E_INVALID
+    assert lib.rg_render(None, 4, 4, None, None) == _native.E_INVALID
+
+
+def test_no_cpu_fallback():
+    """Without a usable GPU scene creation must fail with RG_E_CUDA, never render on the CPU."""
+    lib = _native.lib()
+    if lib.rg_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    desc, keep = example_scene("test2").to_desc()
+    out = ctypes.c_void_p()
+    assert lib.rg_scene_create(ctypes.byref(desc), 0, ctypes.byref(out)) == _native.E_CUDA
+    assert b"no CPU path" in lib.rg_last_error()
+    a = ctypes.c_double()
+    assert lib.rg_measure_peaks(0, ctypes.byref(a), ctypes.byref(a), ctypes.byref(a)) == _native.E_CUDA
+
+
+def test_product_does_not_touch_the_oracle():
+    """oracle/ is test infrastructure: nothing under raingun_b200/ may import, link or load it."""
+    pkg = os.path.join(ROOT, "raingun_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "_build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "raingun_oracle" not in text and "from oracle" not in text and "import oracle" not in text, \
+                    os.path.join(dirpath, f)

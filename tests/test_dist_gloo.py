@@ -1,0 +1,77 @@
+"""The N > 1 host path (row-tile work stealing + gather) on CPU: world_size 2, gloo backend, with
+the CPU oracle standing in for the per-rank renderer.  What is under test is raingun_b200/dist.py:
+tile claiming, row lists, the P2P gather and the reassembled frame."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from raingun_b200.dist import guided_chunks, n_tiles, render_frame_sharded, rows_of_tiles, static_chunk
+
+W, H, TILE = 96, 54, 4
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, schedule, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle
+    from raingun_b200.synth import make_scene
+
+    data, _ = make_scene("C4", spheres=40, depth=4)
+    O = oracle()
+    calls = []
+
+    def render_rowlist(rows, out):
+        # renders each listed row with the oracle; rows are arbitrary, so go row by row
+        buf = np.concatenate([O.render_rows(data, W, H, int(y), int(y) + 1, threads=1)[0] for y in rows], axis=0)
+        out.copy_(torch.from_numpy(buf.reshape(-1)))
+        calls.append(len(rows))
+        return len(rows)
+
+    tiles = []
+    for frame_id in (1, 2):   # two frames: the counter keys must not collide
+        res = render_frame_sharded(render_rowlist, W, H, rank, world, frame_id, torch.device("cpu"),
+                                   tile_rows=TILE, schedule=schedule)
+        tiles.append(sorted(res.my_tiles))
+        if rank == 0:
+            np.save(os.path.join(out_dir, f"frame{frame_id}.npy"), res.frame.numpy())
+    np.save(os.path.join(out_dir, f"tiles{rank}.npy"), np.array(tiles[0], dtype=np.int64))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("schedule", ["steal", "static"])
+def test_two_ranks_reassemble_the_frame(tmp_path, oracle, schedule):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), schedule, str(tmp_path)), nprocs=world, join=True)
+    from raingun_b200.synth import make_scene
+
+    data, _ = make_scene("C4", spheres=40, depth=4)
+    ref, _, _ = oracle.render(data, W, H)
+    for frame_id in (1, 2):
+        assert np.array_equal(np.load(tmp_path / f"frame{frame_id}.npy"), ref)
+    t0, t1 = np.load(tmp_path / "tiles0.npy"), np.load(tmp_path / "tiles1.npy")
+    assert sorted(t0.tolist() + t1.tolist()) == list(range(n_tiles(H, TILE)))   # every tile exactly once
+    if schedule == "static":
+        assert t0.tolist() == static_chunk(n_tiles(H, TILE), 2, 0)
+
+
+def test_schedules_cover_every_tile_once():
+    for nt in (1, 7, 135, 270):
+        for world in (1, 2, 4, 8):
+            chunks = guided_chunks(nt, world)
+            assert [t for c in chunks for t in c] == list(range(nt))
+            assert all(len(a) >= len(b) for a, b in zip(chunks, chunks[1:]))          # large first, small last
+            assert sorted(t for r in range(world) for t in static_chunk(nt, world, r)) == list(range(nt))
+    assert rows_of_tiles([0, 13], 4, 54).tolist() == [0, 1, 2, 3, 52, 53]             # ragged last tile
+    assert rows_of_tiles([], 4, 54).size == 0
