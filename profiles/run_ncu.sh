@@ -1,0 +1,22 @@
+#!/bin/bash
+# Profiling passes of the B200 recipe (/opt/skills/guides/B200_PROFILING.md), run under gpurun:
+#   gpurun --timeout 1500 -- 'bash profiles/run_ncu.sh r01'
+# 1. the plain command must exit 0 first; 2. launch list (gpu__time_duration per launch);
+# 3. one --set full capture of the two trace kernels.  Outputs land in gpurun_out/.
+set -u
+TAG=${1:-r01}
+CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
+mkdir -p gpurun_out
+$CMD > gpurun_out/plain_${TAG}.json 2> gpurun_out/plain_${TAG}.err &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+    --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launch_${TAG}.log 2>&1
+echo "launch list rc=$?"
+$CMD > /dev/null 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_trace_grid -s 2 -c 3 \
+    -o gpurun_out/prof_grid_${TAG} -f $CMD > gpurun_out/ncu_grid_${TAG}.log 2>&1
+echo "grid capture rc=$?"
+$CMD > /dev/null 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_trace_brute -s 0 -c 2 \
+    -o gpurun_out/prof_brute_${TAG} -f $CMD > gpurun_out/ncu_brute_${TAG}.log 2>&1
+echo "brute capture rc=$?"
+ls -la gpurun_out/

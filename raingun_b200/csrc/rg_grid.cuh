@@ -62,12 +62,13 @@ __global__ void __launch_bounds__(kGridTraceThreads) k_trace_grid(const DScene s
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned n_exact = 0, nan_count = 0;
     if (i < a.n) {
-        const Ray ray = load_ray(a.q, i);
+        const uint32_t pi = phys_index(a, i);
+        const Ray ray = load_ray(a.q, pi);
         const GridDev &g = s.grid;
         GridHit<ANY> h;
         h.best.init();
         h.occluded = false;
-        h.tmax = ANY ? a.tmax[i] : 0.0;
+        h.tmax = ANY ? a.tmax[pi] : 0.0;
 
         for (uint32_t m = 0; m < s.n_misc; ++m) {          // planes, disks, boxes: exact, per ray
             const uint32_t b = s.misc_body[m];
@@ -131,8 +132,8 @@ __global__ void __launch_bounds__(kGridTraceThreads) k_trace_grid(const DScene s
                 }
             }
         }
-        if (ANY) a.out_lit[i] = h.occluded ? 0 : 1;
-        else { a.out_t[i] = h.best.t; a.out_body[i] = h.best.body; }
+        if (ANY) a.out_lit[pi] = h.occluded ? 0 : 1;
+        else { a.out_t[pi] = h.best.t; a.out_body[pi] = h.best.body; }
     }
     unsigned long long ne = n_exact;
 #pragma unroll

@@ -5,7 +5,8 @@
 //   * the sphere list is streamed through shared memory in chunks by 1-D bulk async copies
 //     (cp.async.bulk + mbarrier, double-buffered), one 16-byte FP32 cull record per sphere;
 //   * each thread owns R rays (register-tiled), so one broadcast LDS.128 feeds 32*R tests;
-//   * a test is 7 FFMA + 1 FSETP (rg_cull.h): a CONSERVATIVE reject in FP32;
+//   * a test is a CONSERVATIVE reject in FP32 (rg_cull.h); two spheres are tested per
+//     instruction with Blackwell's packed FFMA2 (fma.rn.f32x2): 7 FFMA2 + 2 FSETP per pair;
 //   * the rare survivors are not evaluated in the divergent inner loop: they are appended
 //     to a per-warp candidate queue with __ballot_sync/__popc and evaluated 32 at a time,
 //     one candidate per lane, with the reference's exact FP64 test (rg_exact.cuh);
@@ -35,6 +36,7 @@ struct TraceArgs {
     RayQueue q;
     const double *tmax;      // ANY: light.distance(hit_point) per ray
     uint32_t n;
+    uint32_t seg_len, seg_stride;   // shadow queues are light-major: ray i lives at (i / seg_len) * seg_stride + i % seg_len
     double *out_t;           // nearest: distance (undefined when body == kNoBody)
     uint32_t *out_body;      // nearest: original body index or kNoBody
     uint8_t *out_lit;        // ANY: 1 = in light
@@ -42,6 +44,11 @@ struct TraceArgs {
     int verify;              // RG_OPT_VERIFY_CULL
 };
 
+// Path queues are dense (seg_len = 0).  Shadow queues hold one segment per light so that
+// neighbouring lanes trace neighbouring hits towards the SAME light (coherent directions).
+__device__ __forceinline__ uint32_t phys_index(const TraceArgs &a, uint32_t i) {
+    return a.seg_len ? (i / a.seg_len) * a.seg_stride + (i % a.seg_len) : i;
+}
 __device__ __forceinline__ Ray load_ray(const RayQueue &q, uint32_t i) {
     double2 a = q.a[i], b = q.b[i], c = q.c[i];
     Ray r;
@@ -108,11 +115,47 @@ __device__ __forceinline__ bool cull_reject(const CullRay &c, float4 sp) {
     return g > c.thr;
 }
 
-template <bool ANY, int R>
-__global__ void __launch_bounds__(kTraceThreads, (R >= 4 ? 2 : 3))
+// ---- packed form: two spheres per instruction (sm_100 FFMA2) --------------------------------
+// The brute-force kernel reads the records pair-interleaved: for spheres (2k, 2k+1)
+//     A = (x0, x1, y0, y1)      B = (z0, z1, -K0, -K1)
+// and evaluates h = s*s - q = -g with every per-ray constant of the q-chain negated, which is
+// bit-for-bit the negation of the scalar form (round-to-nearest is symmetric), so
+// "g > thr"  <=>  "h < -thr": the decisions, and the soundness argument, are unchanged.
+struct CullRay2 {
+    float2 dx, dy, dz, nod;     // (d, d), (-(o'.d), -(o'.d))
+    float2 px, py, pz;          // +2 o' duplicated  (= -o2)
+    float nthr;                 // -thr   (-inf: never reject;  +inf: lane without a ray)
+};
+__device__ __forceinline__ CullRay2 make_cull_ray2(const CullRay &c) {
+    CullRay2 p;
+    p.dx = make_float2(c.dx, c.dx); p.dy = make_float2(c.dy, c.dy); p.dz = make_float2(c.dz, c.dz);
+    p.nod = make_float2(c.nod, c.nod);
+    p.px = make_float2(-c.o2x, -c.o2x); p.py = make_float2(-c.o2y, -c.o2y); p.pz = make_float2(-c.o2z, -c.o2z);
+    p.nthr = -c.thr;
+    return p;
+}
+// h for the two spheres of a pair: (h.x < nthr) = sphere 2k rejected, (h.y < nthr) = sphere 2k+1.
+__device__ __forceinline__ float2 cull_h2(const CullRay2 &c, float4 A, float4 B) {
+    const float2 X = make_float2(A.x, A.y), Y = make_float2(A.z, A.w), Z = make_float2(B.x, B.y), NK = make_float2(B.z, B.w);
+    const float2 s = __ffma2_rn(X, c.dx, __ffma2_rn(Y, c.dy, __ffma2_rn(Z, c.dz, c.nod)));
+    const float2 nq = __ffma2_rn(X, c.px, __ffma2_rn(Y, c.py, __ffma2_rn(Z, c.pz, NK)));
+    return __ffma2_rn(s, s, nq);
+}
+// the scalar decision for one sphere of a pair, from the packed constants (rare path)
+__device__ __forceinline__ bool cull_reject_half(const CullRay2 &c, float4 A, float4 B, int half) {
+    const float x = half ? A.y : A.x, y = half ? A.w : A.z, z = half ? B.y : B.x, nk = half ? B.w : B.z;
+    const float s = fmaf(x, c.dx.x, fmaf(y, c.dy.x, fmaf(z, c.dz.x, c.nod.x)));
+    const float nq = fmaf(x, c.px.x, fmaf(y, c.py.x, fmaf(z, c.pz.x, nk)));
+    return fmaf(s, s, nq) < c.nthr;
+}
+
+template <bool ANY, int R, int U, int MINB>
+__global__ void __launch_bounds__(kTraceThreads, MINB)
 k_trace_brute(const DScene s, const TraceArgs a) {
     static_assert(R * kTraceThreads <= (1 << kSlotBits), "slot bits");
-    __shared__ __align__(128) float4 stage[2][kChunkSpheres];
+    static_assert(U == 2 || U == 4, "U spheres = U/2 pairs per iteration");
+    static_assert(kCullPad % U == 0 && U <= kCullPad, "records are padded to kCullPad");
+    __shared__ __align__(128) float4 stage[2][kChunkSpheres + kCullPad];   // + slack for the prefetch
     __shared__ uint64_t mbar[2];
     __shared__ uint32_t cq[kTraceWarps][64];
     __shared__ double best_t[R * kTraceThreads];
@@ -141,11 +184,11 @@ k_trace_brute(const DScene s, const TraceArgs a) {
     if (tid == 0 && nchunks > 0) {
         uint32_t bytes = chunk_records(0) * 16u;
         mbar_expect_tx(&mbar[0], bytes);
-        bulk_g2s(&stage[0][0], s.cull4, bytes, &mbar[0]);
+        bulk_g2s(&stage[0][0], s.cull2, bytes, &mbar[0]);
     }
 
     // ---- prologue: my R rays; the few non-sphere bodies are tested exactly right here
-    CullRay cr[R];
+    CullRay2 cr[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const uint32_t slot = r * kTraceThreads + tid;
@@ -154,13 +197,14 @@ k_trace_brute(const DScene s, const TraceArgs a) {
         Ray ray;
         ray.o = d3(0, 0, 0);
         ray.d = d3(0, 0, 0);
-        if (active) ray = load_ray(a.q, i);
-        cr[r] = make_cull_ray(s, ray, active);
+        const uint32_t pi = active ? phys_index(a, i) : 0u;
+        if (active) ray = load_ray(a.q, pi);
+        cr[r] = make_cull_ray2(make_cull_ray(s, ray, active));
         Nearest best;
         best.init();
         bool occluded = false;
         if (active) {
-            const double tmax = ANY ? a.tmax[i] : 0.0;
+            const double tmax = ANY ? a.tmax[pi] : 0.0;
             for (uint32_t m = 0; m < s.n_misc; ++m) {
                 uint32_t b = s.misc_body[m];
                 double t;
@@ -187,7 +231,7 @@ k_trace_brute(const DScene s, const TraceArgs a) {
             uint32_t e = cq[warp][first + lane];
             slot = e & ((1u << kSlotBits) - 1u);
             sph = e >> kSlotBits;
-            Ray ray = load_ray(a.q, block_base + slot);
+            Ray ray = load_ray(a.q, phys_index(a, block_base + slot));
             double4 sp = s.sph[sph];
             hit = sphere_intersect(sp.x, sp.y, sp.z, sp.w, ray, t);
             ++n_exact;
@@ -197,7 +241,7 @@ k_trace_brute(const DScene s, const TraceArgs a) {
 #endif
         }
         if (ANY) {
-            if (hit && t <= a.tmax[block_base + slot]) best_b[slot] = 1u;   // benign race: all write 1
+            if (hit && t <= a.tmax[phys_index(a, block_base + slot)]) best_b[slot] = 1u;   // benign race: all write 1
         } else {
             const uint32_t body = hit ? s.sph_body[sph] : 0u;
             bool pend = hit;
@@ -225,54 +269,75 @@ k_trace_brute(const DScene s, const TraceArgs a) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             uint32_t bytes = chunk_records(c + 1) * 16u;
             mbar_expect_tx(&mbar[st ^ 1u], bytes);
-            bulk_g2s(&stage[st ^ 1u][0], s.cull4 + (size_t)(c + 1) * kChunkSpheres, bytes, &mbar[st ^ 1u]);
+            bulk_g2s(&stage[st ^ 1u][0], s.cull2 + (size_t)(c + 1) * kChunkSpheres, bytes, &mbar[st ^ 1u]);
         }
         mbar_wait(&mbar[st], (c >> 1) & 1u);
         const uint32_t cnt = chunk_records(c);
         const uint32_t sph_base = c * kChunkSpheres;
         const float4 *sp = stage[st];
-#pragma unroll 1
-        for (uint32_t j = 0; j < cnt; j += 2) {
-            const float4 s0 = sp[j], s1 = sp[j + 1];
-            bool rej[2][R];
-            bool any_pass = a.verify != 0;
+        // Rare path for the group of U records starting at j0: re-run the U*R cull tests (cheaper
+        // than keeping U*R flags live in the hot loop), queue the survivors with warp ballot /
+        // popc compaction, evaluate them exactly 32 at a time.
+        auto survivors = [&](uint32_t j0) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                rej[0][r] = cull_reject(cr[r], s0);
-                rej[1][r] = cull_reject(cr[r], s1);
-                any_pass = any_pass || !rej[0][r] || !rej[1][r];
-            }
-            if (__any_sync(0xffffffffu, any_pass)) {
-                // rare path: find the survivors, queue them (warp ballot / popc compaction)
+            for (int u = 0; u < U; ++u) {
+                const uint32_t sph = sph_base + j0 + u;
+                const float4 A = sp[(j0 + u) & ~1u], B = sp[((j0 + u) & ~1u) + 1];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const uint32_t sph = sph_base + j + u;
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const uint32_t slot = r * kTraceThreads + tid;
-                        const bool live = (block_base + slot < a.n) && sph < nsph;
-                        const bool pass = live && !rej[u][r];
-                        if (a.verify && live && rej[u][r]) {   // debug: a culled pair must miss exactly
-                            Ray ray = load_ray(a.q, block_base + slot);
-                            double4 e = s.sph[sph];
-                            double t;
-                            if (sphere_intersect(e.x, e.y, e.z, e.w, ray, t)) ++unsound;
-                        }
-                        const uint32_t mask = __ballot_sync(0xffffffffu, pass);
-                        if (mask) {
-                            if (pass) cq[warp][qn + __popc(mask & lanemask_lt)] = (sph << kSlotBits) | slot;
-                            qn += __popc(mask);
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t slot = r * kTraceThreads + tid;
+                    const bool live = (block_base + slot < a.n) && sph < nsph;
+                    const bool rej = cull_reject_half(cr[r], A, B, (j0 + u) & 1);
+                    const bool pass = live && !rej;
+                    if (a.verify && live && rej) {   // debug: a culled pair must miss exactly
+                        Ray ray = load_ray(a.q, phys_index(a, block_base + slot));
+                        double4 e = s.sph[sph];
+                        double t;
+                        if (sphere_intersect(e.x, e.y, e.z, e.w, ray, t)) ++unsound;
+                    }
+                    const uint32_t mask = __ballot_sync(0xffffffffu, pass);
+                    if (mask) {
+                        if (pass) cq[warp][qn + __popc(mask & lanemask_lt)] = (sph << kSlotBits) | slot;
+                        qn += __popc(mask);
+                        __syncwarp();
+                        if (qn >= 32u) {
+                            drain(qn - 32u, 32u);
+                            qn -= 32u;
                             __syncwarp();
-                            if (qn >= 32u) {
-                                drain(qn - 32u, 32u);
-                                qn -= 32u;
-                                __syncwarp();
-                            }
                         }
                     }
                 }
             }
+        };
+        // Hot loop.  The "did anything survive" vote of group j is taken one iteration late, so
+        // the FSETP -> VOTE -> BRA latency chain overlaps the next group's FFMAs instead of
+        // stalling the warp at the bottom of every iteration.
+        float4 sv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) sv[u] = sp[u];
+        bool prev_pass = false;
+#pragma unroll 1
+        for (uint32_t j = 0; j < cnt; j += U) {
+            float4 sc[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) sc[u] = sv[u];
+            // software prefetch of the next U records (the stage has kCullPad records of slack)
+#pragma unroll
+            for (int u = 0; u < U; ++u) sv[u] = sp[j + U + u];
+            const bool vote_prev = __any_sync(0xffffffffu, prev_pass);
+            bool any_pass = a.verify != 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                for (int u = 0; u < U; u += 2) {
+                    const float2 h = cull_h2(cr[r], sc[u], sc[u + 1]);
+                    any_pass = any_pass | !(h.x < cr[r].nthr) | !(h.y < cr[r].nthr);   // `|`: no short-circuit branches
+                }
+            }
+            if (vote_prev) survivors(j - U);
+            prev_pass = any_pass;
         }
+        if (cnt && __any_sync(0xffffffffu, prev_pass)) survivors(cnt - U);
         __syncthreads();   // everyone is done with stage[st] before it is refilled
     }
     if (qn) drain(0u, qn);
@@ -284,8 +349,9 @@ k_trace_brute(const DScene s, const TraceArgs a) {
         const uint32_t slot = r * kTraceThreads + tid;
         const uint32_t i = block_base + slot;
         if (i < a.n) {
-            if (ANY) a.out_lit[i] = best_b[slot] ? 0 : 1;
-            else { a.out_t[i] = best_t[slot]; a.out_body[i] = best_b[slot]; }
+            const uint32_t pi = phys_index(a, i);
+            if (ANY) a.out_lit[pi] = best_b[slot] ? 0 : 1;
+            else { a.out_t[pi] = best_t[slot]; a.out_body[pi] = best_b[slot]; }
         }
     }
 #pragma unroll

@@ -16,6 +16,7 @@
 // the reference's order and the image is bit-identical to the recursive evaluation —
 // no throughput-weight reformulation, no atomics on pixels.
 #include <algorithm>
+#include <cstdlib>
 
 #include "rg_grid.cuh"
 #include "rg_host.h"
@@ -37,6 +38,7 @@ struct LevelBuffers {
     float4 *lit_bc;
     uint32_t *lit_node;
     uint32_t n;
+    uint32_t shadow_sl, shadow_sj;   // shadow ray of (lit hit j, light l) lives at l * shadow_sl + j * shadow_sj
     uint32_t can_spawn;    // depth + 1 < max_recursion_depth
 };
 
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(256) k_shade(const DScene s, const LevelBuffer
         for (uint32_t l = 0; l < s.n_lights; ++l) {
             const DLight &L = s.lights[l];
             sh.d = light_direction_from(L, hp);
-            const uint32_t k = j * s.n_lights + l;
+            const uint32_t k = l * lb.shadow_sl + j * lb.shadow_sj;
             store_ray(lb.shadow, k, sh);
             lb.s_tmax[k] = light_distance(L, hp);
             lb.s_ab[k] = make_float2(fmaxf((float)dot(n, sh.d), 0.0f), light_intensity(L, hp));
@@ -145,14 +147,15 @@ __global__ void __launch_bounds__(256) k_shade(const DScene s, const LevelBuffer
 // rendering.rs:140,157-171: final_color accumulates light by light, in scene order, then clamps.
 __global__ void __launch_bounds__(256) k_diffuse(const DScene s, const float4 *__restrict__ lit_bc,
                                                  const uint32_t *__restrict__ lit_node, const float2 *__restrict__ s_ab,
-                                                 const uint8_t *__restrict__ s_lit, float4 *node_a, uint32_t n_lit) {
+                                                 const uint8_t *__restrict__ s_lit, float4 *node_a, uint32_t n_lit,
+                                                 uint32_t shadow_sl, uint32_t shadow_sj) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_lit) return;
     const float4 b = lit_bc[j];
     const C3 bc = c3(b.x, b.y, b.z);
     C3 fin = c3(0.0f, 0.0f, 0.0f);
     for (uint32_t l = 0; l < s.n_lights; ++l) {
-        const uint32_t k = j * s.n_lights + l;
+        const uint32_t k = l * shadow_sl + j * shadow_sj;
         const float2 ab = s_ab[k];
         fin = fin + light_term(bc, s.lights[l], b.w, ab.x, ab.y, s_lit[k] != 0);
     }
@@ -207,21 +210,22 @@ template <bool ANY>
 __global__ void __launch_bounds__(128) k_verify_trace(const DScene s, const TraceArgs a, int level) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    const Ray ray = load_ray(a.q, i);
+    const uint32_t pi = phys_index(a, i);
+    const Ray ray = load_ray(a.q, pi);
     const Nearest h = trace_exact_all(s, ray, a.ctr);
     bool bad;
     if (ANY) {
-        const bool lit = !h.found() || h.t > a.tmax[i];
-        bad = (a.out_lit[i] != 0) != lit;
+        const bool lit = !h.found() || h.t > a.tmax[pi];
+        bad = (a.out_lit[pi] != 0) != lit;
     } else {
-        bad = a.out_body[i] != h.body || (h.found() && a.out_t[i] != h.t);
+        bad = a.out_body[pi] != h.body || (h.found() && a.out_t[pi] != h.t);
     }
     if (bad) {
         unsigned long long k = atomicAdd(&a.ctr->cull_unsound, 1ull);
         if (k < 8)
             printf("verify: level %d %s ray %u o=(%.17g,%.17g,%.17g) d=(%.17g,%.17g,%.17g) exact=(%.17g,%u) got=(%.17g,%u)\n", level,
                    ANY ? "shadow" : "path", i, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, h.t, h.body,
-                   ANY ? (double)a.out_lit[i] : a.out_t[i], ANY ? 0u : a.out_body[i]);
+                   ANY ? (double)a.out_lit[pi] : a.out_t[pi], ANY ? 0u : a.out_body[pi]);
     }
 }
 
@@ -256,13 +260,27 @@ static int launch_trace(rg_scene *sc, const TraceArgs &ta, bool use_grid, cudaSt
     } else {
         // register tiling R: 4 rays per thread when there is enough work to fill the chip
         const uint64_t full = (uint64_t)sc->sm_count * 2 * kTraceThreads;
+        static const int variant = [] { const char *e = getenv("RG_BRUTE_VARIANT"); return e ? atoi(e) : 0; }();
+#define RG_LAUNCH_BRUTE(R_, U_, M_) \
+    k_trace_brute<ANY, R_, U_, M_><<<(ta.n + R_ * kTraceThreads - 1) / (R_ * kTraceThreads), kTraceThreads, 0, stream>>>(sc->ds, ta)
         if (ta.n >= full * 4 * 2) {
-            k_trace_brute<ANY, 4><<<(ta.n + 4 * kTraceThreads - 1) / (4 * kTraceThreads), kTraceThreads, 0, stream>>>(sc->ds, ta);
+            switch (variant) {
+                case 1: RG_LAUNCH_BRUTE(4, 4, 2); break;
+                case 2: RG_LAUNCH_BRUTE(2, 2, 3); break;
+                case 3: RG_LAUNCH_BRUTE(2, 4, 3); break;
+                case 4: RG_LAUNCH_BRUTE(2, 4, 4); break;
+                case 5: RG_LAUNCH_BRUTE(2, 2, 4); break;
+                case 6: RG_LAUNCH_BRUTE(4, 2, 3); break;
+                case 7: RG_LAUNCH_BRUTE(4, 4, 3); break;
+                case 8: RG_LAUNCH_BRUTE(4, 2, 2); break;
+                default: RG_LAUNCH_BRUTE(2, 4, 4); break;
+            }
         } else if (ta.n >= full * 2 * 2) {
-            k_trace_brute<ANY, 2><<<(ta.n + 2 * kTraceThreads - 1) / (2 * kTraceThreads), kTraceThreads, 0, stream>>>(sc->ds, ta);
+            RG_LAUNCH_BRUTE(2, 4, 4);
         } else {
-            k_trace_brute<ANY, 1><<<(ta.n + kTraceThreads - 1) / kTraceThreads, kTraceThreads, 0, stream>>>(sc->ds, ta);
+            RG_LAUNCH_BRUTE(1, 2, 3);
         }
+#undef RG_LAUNCH_BRUTE
     }
     RG_CUDA(cudaGetLastError());
     return RG_OK;
@@ -341,6 +359,10 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
         lb.lit_bc = wf.lit_bc.as<float4>();
         lb.lit_node = wf.lit_node.as<uint32_t>();
         lb.n = n;
+        // shadow-queue order: hit-major (the L rays of a hit adjacent; default) or light-major
+        static const bool light_major = [] { const char *e = getenv("RG_SHADOW_LIGHT_MAJOR"); return e && atoi(e) != 0; }();
+        lb.shadow_sl = light_major ? n : 1u;
+        lb.shadow_sj = light_major ? 1u : L;
         lb.can_spawn = can_spawn ? 1u : 0u;
         RG_CUDA(cudaMemsetAsync(&dc->q_next, 0, 2 * sizeof(unsigned int), stream));
         k_shade<<<blocks(n), 256, 0, stream>>>(ds, lb, dc);
@@ -355,6 +377,8 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
             sa.q = lb.shadow;
             sa.tmax = lb.s_tmax;
             sa.n = n_lit * L;
+            sa.seg_len = light_major ? n_lit : 0u;
+            sa.seg_stride = n;
             sa.out_lit = wf.s_lit.as<uint8_t>();
             sa.ctr = dc;
             sa.verify = sc->verify_cull == 1;
@@ -369,7 +393,7 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
         }
         if (n_lit) {
             k_diffuse<<<blocks(n_lit), 256, 0, stream>>>(ds, lb.lit_bc, lb.lit_node, lb.s_ab, wf.s_lit.as<uint8_t>(),
-                                                         lb.node_a, n_lit);
+                                                         lb.node_a, n_lit, lb.shadow_sl, lb.shadow_sj);
             RG_CUDA(cudaGetLastError());
             st->gpu_launches++;
         }
