@@ -18,6 +18,16 @@
 //     un-normalised plane normals — non-finite or far-away origins) skip the grid and scan
 //     every sphere exactly;
 //   * spheres too large for the grid ("loose") and all non-sphere bodies are tested per ray.
+//
+// Execution model.  Ray lengths differ wildly (a lit shadow ray crosses the whole grid, an
+// occluded one stops after a few cells) and the exact FP64 test is ~10x a cull test, so a
+// one-thread-per-ray loop leaves most lanes of a warp idle (measured: 6 of 32 active).  The
+// kernel therefore runs PERSISTENT warps:
+//   * lanes whose ray is finished fetch new rays from a global counter (warp ballot + one
+//     atomic per refill) instead of waiting for the slowest lane;
+//   * a lane that finds a cull survivor parks it ("pending") and keeps nothing else going;
+//     the warp evaluates pending candidates together, so the expensive exact test runs with
+//     many lanes active instead of one.
 #pragma once
 #include "rg_trace.cuh"
 
@@ -27,6 +37,18 @@ constexpr int kGridTraceThreads = 128;
 constexpr float kGridInflate = 2e-3f;       // in cells; see above
 constexpr float kGridMaxCoord = 2048.0f;    // |grid coordinate| limit for FP32 traversal
 constexpr double kGridUnitTol = 1e-9;
+constexpr int kGridRefill = 12;             // refill when at least this many lanes are idle
+constexpr int kGridExactQuorum = 10;        // evaluate pending candidates when this many lanes wait
+constexpr int kGridScanBurst = 4;           // scan steps between quorum checks
+#ifndef RG_GRID_PREFETCH
+#define RG_GRID_PREFETCH 0
+#endif
+#ifndef RG_GRID_MINB
+#define RG_GRID_MINB 6
+#endif
+constexpr bool kGridPrefetch = RG_GRID_PREFETCH != 0;   // speculative fetch of the next cell's record
+constexpr uint32_t kNoSphere = 0xFFFFFFFFu;
+constexpr float kFltBig = 3.4e38f;
 
 template <bool ANY>
 struct GridHit {
@@ -39,15 +61,14 @@ struct GridHit {
     }
     // upper bound on distances still worth looking at (FP32, rounded up generously)
     __device__ __forceinline__ float bound() const {
-        if (ANY) return tmax < 3.0e38 ? (float)tmax * 1.000001f + 1e-30f : 3.4e38f;
-        return best.found() ? (float)best.t * 1.000001f + 1e-30f : 3.4e38f;
+        if (ANY) return tmax < 3.0e38 ? (float)tmax * 1.000001f + 1e-30f : kFltBig;
+        return best.found() ? (float)best.t * 1.000001f + 1e-30f : kFltBig;
     }
 };
 
 template <bool ANY>
-__device__ __forceinline__ void test_sphere(const DScene &s, const Ray &ray, const CullRay &cr, uint32_t sph,
-                                            float4 rec, GridHit<ANY> &h, unsigned &n_exact, unsigned &nan_count) {
-    if (cull_reject(cr, rec)) return;
+__device__ __forceinline__ void exact_sphere(const DScene &s, const Ray &ray, uint32_t sph, GridHit<ANY> &h,
+                                             unsigned &n_exact, unsigned &nan_count) {
     const double4 sp = s.sph[sph];
     double t;
     ++n_exact;
@@ -58,90 +79,267 @@ __device__ __forceinline__ void test_sphere(const DScene &s, const Ray &ray, con
 }
 
 template <bool ANY>
-__global__ void __launch_bounds__(kGridTraceThreads) k_trace_grid(const DScene s, const TraceArgs a) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(const DScene s, const TraceArgs a) {
+    const GridDev &g = s.grid;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lanemask_lt = (1u << lane) - 1u;
     unsigned n_exact = 0, nan_count = 0;
-    if (i < a.n) {
-        const uint32_t pi = phys_index(a, i);
-        const Ray ray = load_ray(a.q, pi);
-        const GridDev &g = s.grid;
-        GridHit<ANY> h;
-        h.best.init();
-        h.occluded = false;
-        h.tmax = ANY ? a.tmax[pi] : 0.0;
 
-        for (uint32_t m = 0; m < s.n_misc; ++m) {          // planes, disks, boxes: exact, per ray
-            const uint32_t b = s.misc_body[m];
-            double t;
-            if (misc_intersect(s, b, ray, t)) {
-                if (t != t) { ++nan_count; continue; }
-                h.offer(t, b);
-            }
+    // ---- per-lane ray state
+    bool active = false;        // this lane owns an unfinished ray
+    bool walking = false;       // ... and it is inside the grid walk (else it only waits to be written out)
+    uint32_t pi = 0;            // physical queue index of the ray
+    CullRay cr;
+    GridHit<ANY> h;
+    float ogx = 0, ogy = 0, ogz = 0, ix = 0, iy = 0, iz = 0;   // grid-space origin, 1 / direction
+    float fbx = 0, fby = 0, fbz = 0;                           // next cell boundary per axis (grid coords)
+    float tnx = 0, tny = 0, tnz = 0;                           // ray parameter at those boundaries
+    float sxf = 0, syf = 0, szf = 0;                           // +-1 step per axis (0: never steps)
+    float t0f = 0;                                             // the walk is parameterised from o + t0*d (far origins)
+    int cx = 0, cy = 0, cz = 0;
+    int cell = 0, scx = 0, scy = 0, scz = 0;                   // linear cell index and its per-axis stride (signed)
+    uint32_t pend0 = kNoSphere, pend1 = kNoSphere;             // cull survivors waiting for their exact test
+    bool fresh = false;                                        // the current cell's record has not been examined yet
+    float4 c0, c1, n0, n1;                                     // cull records of the current / prefetched next cell
+    uint4 cm, nm;                                              // ... and their (idx0, idx1, overflow begin, end)
+    bool exhausted = false;                                    // warp-uniform: the queue has no more rays
+    h.best.init();
+    h.occluded = false;
+    h.tmax = 0.0;
+    c0 = c1 = n0 = n1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    cm = nm = make_uint4(kNoSphere, kNoSphere, 0u, 0u);
+    {
+        Ray none;
+        none.o = d3(0, 0, 0);
+        none.d = d3(0, 0, 0);
+        cr = make_cull_ray(s, none, false);
+    }
+
+
+    // Speculative fetch of the record of the cell the walk would enter next (the axis choice
+    // depends only on the boundary parameters, not on the outcome of the current cell's tests),
+    // so the dependent-load latency of a step overlaps the culls / exact tests of this cell.
+    auto prefetch_next = [&]() {
+        if (!kGridPrefetch) return;
+        const bool ax = tnx <= tny && tnx <= tnz;
+        const bool ay = !ax && tny <= tnz;
+        const int ncx = cx + (ax ? (int)sxf : 0), ncy = cy + (ay ? (int)syf : 0), ncz = cz + ((!ax && !ay) ? (int)szf : 0);
+        const bool inside = (unsigned)ncx < (unsigned)g.dim[0] && (unsigned)ncy < (unsigned)g.dim[1] &&
+                            (unsigned)ncz < (unsigned)g.dim[2];
+        if (inside) {
+            const float4 *rec = g.cell_rec + 3 * (size_t)(cell + (ax ? scx : (ay ? scy : scz)));
+            n0 = rec[0];
+            n1 = rec[1];
+            nm = *reinterpret_cast<const uint4 *>(rec + 2);
         }
-        n_exact += s.n_misc;
+    };
 
-        const CullRay cr = make_cull_ray(s, ray, true);
-        const D3 op = ray.o - d3(s.cull_ref[0], s.cull_ref[1], s.cull_ref[2]);
-        const double D2 = dot(ray.d, ray.d);
-        // grid-space ray (FP32): cells are unit cubes
-        const float ogx = ((float)op.x - g.lo[0]) * g.inv_cell[0], ogy = ((float)op.y - g.lo[1]) * g.inv_cell[1],
-                    ogz = ((float)op.z - g.lo[2]) * g.inv_cell[2];
-        const float dgx = (float)ray.d.x * g.inv_cell[0], dgy = (float)ray.d.y * g.inv_cell[1],
-                    dgz = (float)ray.d.z * g.inv_cell[2];
-        const bool walkable = fabs(D2 - 1.0) <= kGridUnitTol && fabsf(ogx) <= kGridMaxCoord &&
-                              fabsf(ogy) <= kGridMaxCoord && fabsf(ogz) <= kGridMaxCoord;   // false on NaN
-        if (!walkable) {
-            if (!(ANY && h.occluded))
-                for (uint32_t k = 0; k < s.n_spheres; ++k) test_sphere<ANY>(s, ray, cr, k, s.cull4[k], h, n_exact, nan_count);
-        } else if (!(ANY && h.occluded)) {
-            for (uint32_t k = 0; k < g.n_loose; ++k) { const uint32_t sp = g.loose[k]; test_sphere<ANY>(s, ray, cr, sp, s.cull4[sp], h, n_exact, nan_count); }
-            // clip the ray to the grid box [0, dim] (slabs; a zero component gives +-inf, handled by min/max)
-            const float ix = 1.0f / dgx, iy = 1.0f / dgy, iz = 1.0f / dgz;
-            const float dimx = (float)g.dim[0], dimy = (float)g.dim[1], dimz = (float)g.dim[2];
-            float t0x = (0.0f - ogx) * ix, t1x = (dimx - ogx) * ix;
-            float t0y = (0.0f - ogy) * iy, t1y = (dimy - ogy) * iy;
-            float t0z = (0.0f - ogz) * iz, t1z = (dimz - ogz) * iz;
-            // a ray parallel to a slab (d = 0): inside -> (-inf, +inf), outside -> empty
-            if (dgx == 0.0f) { bool in = ogx >= 0.0f && ogx <= dimx; t0x = in ? -3.4e38f : 3.4e38f; t1x = in ? 3.4e38f : -3.4e38f; }
-            if (dgy == 0.0f) { bool in = ogy >= 0.0f && ogy <= dimy; t0y = in ? -3.4e38f : 3.4e38f; t1y = in ? 3.4e38f : -3.4e38f; }
-            if (dgz == 0.0f) { bool in = ogz >= 0.0f && ogz <= dimz; t0z = in ? -3.4e38f : 3.4e38f; t1z = in ? 3.4e38f : -3.4e38f; }
-            float tenter = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
-            float texit = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-            // slack: the box walls are kGridInflate-padded away from every sphere, so nudging inwards is safe
-            if (tenter <= texit * 1.000001f + 1e-6f && tenter <= h.bound()) {
-                const float ts = tenter;
-                int cx = min(max((int)floorf(ogx + ts * dgx), 0), g.dim[0] - 1);
-                int cy = min(max((int)floorf(ogy + ts * dgy), 0), g.dim[1] - 1);
-                int cz = min(max((int)floorf(ogz + ts * dgz), 0), g.dim[2] - 1);
-                const int sx = dgx > 0.0f ? 1 : -1, sy = dgy > 0.0f ? 1 : -1, sz = dgz > 0.0f ? 1 : -1;
-                for (;;) {
-                    // parameter at which the ray leaves this cell, per axis (recomputed, not accumulated)
-                    const float nx = dgx != 0.0f ? ((float)(cx + (sx > 0)) - ogx) * ix : 3.4e38f;
-                    const float ny = dgy != 0.0f ? ((float)(cy + (sy > 0)) - ogy) * iy : 3.4e38f;
-                    const float nz = dgz != 0.0f ? ((float)(cz + (sz > 0)) - ogz) * iz : 3.4e38f;
-                    const float tnext = fminf(nx, fminf(ny, nz));
-                    const uint32_t cell = ((uint32_t)cz * (uint32_t)g.dim[1] + (uint32_t)cy) * (uint32_t)g.dim[0] + (uint32_t)cx;
-                    const uint32_t b0 = g.cell_start[cell], b1 = g.cell_start[cell + 1];
-                    for (uint32_t k = b0; k < b1; ++k) test_sphere<ANY>(s, ray, cr, g.cell_items[k], g.cell_cull4[k], h, n_exact, nan_count);
-                    if (ANY && h.occluded) break;
-                    // everything nearer than the cell exit has been seen: done (slack for FP32 t error)
-                    if (h.bound() < tnext * 0.99999f - 1e-5f) break;
-                    if (nx <= ny && nx <= nz) { cx += sx; if ((unsigned)cx >= (unsigned)g.dim[0]) break; }
-                    else if (ny <= nz) { cy += sy; if ((unsigned)cy >= (unsigned)g.dim[1]) break; }
-                    else { cz += sz; if ((unsigned)cz >= (unsigned)g.dim[2]) break; }
+    for (;;) {
+        // ================= (A) refill idle lanes from the global ray counter =================
+        const uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (idle == 0xffffffffu && exhausted) break;
+        if (!exhausted && (__popc(idle) >= a.g_refill)) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&a.ctr->fetch, (unsigned)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            exhausted = base + (uint32_t)__popc(idle) >= a.n;
+            const uint32_t ri = base + __popc(idle & lanemask_lt);
+            if (!active && ri < a.n) {
+                // ---- set a new ray up: non-sphere bodies, loose spheres, clip to the grid
+                active = true;
+                walking = false;
+                pend0 = pend1 = kNoSphere;
+                fresh = false;
+                pi = phys_index(a, ri);
+                const Ray ray = load_ray(a.q, pi);
+                h.best.init();
+                h.occluded = false;
+                h.tmax = ANY ? a.tmax[pi] : 0.0;
+                for (uint32_t m = 0; m < s.n_misc; ++m) {          // planes, disks, boxes: exact, per ray
+                    const uint32_t b = s.misc_body[m];
+                    double t;
+                    if (misc_intersect(s, b, ray, t)) {
+                        if (t != t) { ++nan_count; continue; }
+                        h.offer(t, b);
+                    }
+                }
+                n_exact += s.n_misc;
+                cr = make_cull_ray(s, ray, true);
+                D3 op = ray.o - d3(s.cull_ref[0], s.cull_ref[1], s.cull_ref[2]);
+                const double D2 = dot(ray.d, ray.d);
+                // Far-away origins (e.g. hits on an infinite plane near the horizon) would lose FP32
+                // position accuracy inside the grid.  Clip such rays against the grid box in FP64 and
+                // start the FP32 walk from o + t0*d, a point on the same ray just before the box.
+                bool misses_box = false;
+                t0f = 0.0f;
+                {
+                    const double gx = (op.x - (double)g.lo[0]) * (double)g.inv_cell[0];
+                    const double gy = (op.y - (double)g.lo[1]) * (double)g.inv_cell[1];
+                    const double gz = (op.z - (double)g.lo[2]) * (double)g.inv_cell[2];
+                    const double lim = 0.5 * (double)kGridMaxCoord;
+                    const bool near_box = fabs(gx) <= lim && fabs(gy) <= lim && fabs(gz) <= lim;   // false on NaN
+                    const bool finite = fabs(gx) < 1e30 && fabs(gy) < 1e30 && fabs(gz) < 1e30;
+                    if (!near_box && finite) {
+                        const double ddx = ray.d.x * (double)g.inv_cell[0], ddy = ray.d.y * (double)g.inv_cell[1],
+                                     ddz = ray.d.z * (double)g.inv_cell[2];
+                        double tmin = 0.0, tmax = 1e300;
+                        const double gs[3] = {gx, gy, gz}, ds[3] = {ddx, ddy, ddz};
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const double dimk = (double)g.dim[k];
+                            if (ds[k] == 0.0) {
+                                if (gs[k] < -1.0 || gs[k] > dimk + 1.0) misses_box = true;
+                            } else {
+                                const double ta = (-1.0 - gs[k]) / ds[k], tb = (dimk + 1.0 - gs[k]) / ds[k];   // box padded by a cell
+                                tmin = fmax(tmin, fmin(ta, tb));
+                                tmax = fmin(tmax, fmax(ta, tb));
+                            }
+                        }
+                        if (!(tmin <= tmax)) misses_box = true;   // also on NaN
+                        if (!misses_box) {
+                            op = op + ray.d * tmin;                // still on the ray, one cell before the box
+                            t0f = __double2float_rd(tmin);         // rounded down: bounds stay conservative
+                        }
+                    }
+                }
+                ogx = ((float)op.x - g.lo[0]) * g.inv_cell[0];
+                ogy = ((float)op.y - g.lo[1]) * g.inv_cell[1];
+                ogz = ((float)op.z - g.lo[2]) * g.inv_cell[2];
+                const float dgx = (float)ray.d.x * g.inv_cell[0], dgy = (float)ray.d.y * g.inv_cell[1],
+                            dgz = (float)ray.d.z * g.inv_cell[2];
+                const bool walkable = fabs(D2 - 1.0) <= kGridUnitTol && (misses_box || (fabsf(ogx) <= kGridMaxCoord &&
+                                      fabsf(ogy) <= kGridMaxCoord && fabsf(ogz) <= kGridMaxCoord));   // false on NaN
+                if (!(ANY && h.occluded)) {
+                    if (!walkable) {
+                        // outside the conservativeness argument: scan every sphere (cull + exact)
+                        for (uint32_t q = 0; q < s.n_spheres; ++q)
+                            if (!cull_reject(cr, s.cull4[q])) exact_sphere<ANY>(s, ray, q, h, n_exact, nan_count);
+                    } else {
+                        for (uint32_t q = 0; q < g.n_loose; ++q) {
+                            const uint32_t sp = g.loose[q];
+                            if (!cull_reject(cr, s.cull4[sp])) exact_sphere<ANY>(s, ray, sp, h, n_exact, nan_count);
+                        }
+                        // clip the ray to the grid box [0, dim]
+                        ix = 1.0f / dgx; iy = 1.0f / dgy; iz = 1.0f / dgz;
+                        const float dimx = (float)g.dim[0], dimy = (float)g.dim[1], dimz = (float)g.dim[2];
+                        float t0x = (0.0f - ogx) * ix, t1x = (dimx - ogx) * ix;
+                        float t0y = (0.0f - ogy) * iy, t1y = (dimy - ogy) * iy;
+                        float t0z = (0.0f - ogz) * iz, t1z = (dimz - ogz) * iz;
+                        // a ray parallel to a slab (d = 0): inside -> (-inf, +inf), outside -> empty
+                        if (dgx == 0.0f) { bool in = ogx >= 0.0f && ogx <= dimx; t0x = in ? -kFltBig : kFltBig; t1x = in ? kFltBig : -kFltBig; }
+                        if (dgy == 0.0f) { bool in = ogy >= 0.0f && ogy <= dimy; t0y = in ? -kFltBig : kFltBig; t1y = in ? kFltBig : -kFltBig; }
+                        if (dgz == 0.0f) { bool in = ogz >= 0.0f && ogz <= dimz; t0z = in ? -kFltBig : kFltBig; t1z = in ? kFltBig : -kFltBig; }
+                        const float tenter = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+                        const float texit = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+                        // slack: the box walls are padded away from every sphere, so grazing rays may go either way
+                        if (!misses_box && tenter <= texit * 1.000001f + 1e-6f && tenter <= h.bound() - t0f) {
+                            cx = min(max((int)floorf(ogx + tenter * dgx), 0), g.dim[0] - 1);
+                            cy = min(max((int)floorf(ogy + tenter * dgy), 0), g.dim[1] - 1);
+                            cz = min(max((int)floorf(ogz + tenter * dgz), 0), g.dim[2] - 1);
+                            sxf = dgx > 0.0f ? 1.0f : (dgx < 0.0f ? -1.0f : 0.0f);
+                            syf = dgy > 0.0f ? 1.0f : (dgy < 0.0f ? -1.0f : 0.0f);
+                            szf = dgz > 0.0f ? 1.0f : (dgz < 0.0f ? -1.0f : 0.0f);
+                            // exit boundary of the start cell per axis; the parameter there is recomputed from the
+                            // boundary coordinate at every step (never accumulated)
+                            fbx = (float)(cx + (sxf > 0.0f));
+                            fby = (float)(cy + (syf > 0.0f));
+                            fbz = (float)(cz + (szf > 0.0f));
+                            tnx = sxf != 0.0f ? (fbx - ogx) * ix : kFltBig;
+                            tny = syf != 0.0f ? (fby - ogy) * iy : kFltBig;
+                            tnz = szf != 0.0f ? (fbz - ogz) * iz : kFltBig;
+                            cell = (cz * g.dim[1] + cy) * g.dim[0] + cx;
+                            scx = (int)sxf; scy = (int)syf * g.dim[0]; scz = (int)szf * g.dim[0] * g.dim[1];
+                            walking = true;
+                            fresh = true;
+                            {
+                                const float4 *rec = g.cell_rec + 3 * (size_t)cell;
+                                c0 = rec[0];
+                                c1 = rec[1];
+                                cm = *reinterpret_cast<const uint4 *>(rec + 2);
+                            }
+                            prefetch_next();
+                        }
+                    }
                 }
             }
         }
-        if (ANY) a.out_lit[pi] = h.occluded ? 0 : 1;
-        else { a.out_t[pi] = h.best.t; a.out_body[pi] = h.best.body; }
+
+        // ================= (B) scan: one cell per step — fetch its record, cull its two inline items ====
+#pragma unroll 1
+        for (int burst = 0; burst < a.g_burst; ++burst) {
+            const bool go = active && pend0 == kNoSphere && pend1 == kNoSphere;
+            if (go && walking) {
+                if (fresh) {
+                    // examine the current cell: two inline items, rarely an overflow list
+                    if (cm.x != kNoSphere && !cull_reject(cr, c0)) pend0 = cm.x;
+                    if (cm.y != kNoSphere && !cull_reject(cr, c1)) pend1 = cm.y;
+                    if (cm.w) {   // > 2 items: the rest of the list, exact tests inline (rare)
+                        const Ray ray = load_ray(a.q, pi);
+                        for (uint32_t q = cm.z; q < cm.w; ++q)
+                            if (!cull_reject(cr, g.cell_cull4[q])) exact_sphere<ANY>(s, ray, g.cell_items[q], h, n_exact, nan_count);
+                    }
+                    fresh = false;
+                }
+                if (pend0 == kNoSphere && pend1 == kNoSphere) {
+                    // every item of the current cell is decided: stop, or step to the next cell
+                    // (branch-free axis choice; its record was prefetched)
+                    const float tnext = fminf(tnx, fminf(tny, tnz));
+                    bool stop = (ANY && h.occluded) || (h.bound() - t0f < tnext * 0.99999f - 1e-5f);
+                    const bool ax = tnx <= tny && tnx <= tnz;
+                    const bool ay = !ax && tny <= tnz;
+                    const bool az = !ax && !ay;
+                    cx += ax ? (int)sxf : 0; cy += ay ? (int)syf : 0; cz += az ? (int)szf : 0;
+                    fbx += ax ? sxf : 0.0f; fby += ay ? syf : 0.0f; fbz += az ? szf : 0.0f;
+                    tnx = ax ? (fbx - ogx) * ix : tnx;
+                    tny = ay ? (fby - ogy) * iy : tny;
+                    tnz = az ? (fbz - ogz) * iz : tnz;
+                    cell += ax ? scx : (ay ? scy : scz);
+                    stop = stop || (unsigned)cx >= (unsigned)g.dim[0] || (unsigned)cy >= (unsigned)g.dim[1] ||
+                           (unsigned)cz >= (unsigned)g.dim[2];
+                    walking = !stop;
+                    if (walking) {
+                        if (kGridPrefetch) { c0 = n0; c1 = n1; cm = nm; }
+                        else {
+                            const float4 *rec = g.cell_rec + 3 * (size_t)cell;
+                            c0 = rec[0];
+                            c1 = rec[1];
+                            cm = *reinterpret_cast<const uint4 *>(rec + 2);
+                        }
+                        fresh = true;
+                        prefetch_next();
+                    }
+                }
+            }
+            if (go && !walking && pend0 == kNoSphere && pend1 == kNoSphere) {
+                // ---- finished: write the result, free the lane
+                if (ANY) a.out_lit[pi] = h.occluded ? 0 : 1;
+                else { a.out_t[pi] = h.best.t; a.out_body[pi] = h.best.body; }
+                active = false;
+            }
+        }
+
+        // ================= (C) exact tests of the parked candidates, many lanes at a time ==========
+        const bool has_pending = pend0 != kNoSphere || pend1 != kNoSphere;
+        const uint32_t waiting = __ballot_sync(0xffffffffu, has_pending);
+        const uint32_t scanning = __ballot_sync(0xffffffffu, active && !has_pending);
+        if (waiting && (__popc(waiting) >= a.g_quorum || scanning == 0u ||
+                        (exhausted && __popc(waiting) * 2 >= __popc(waiting | scanning)))) {
+            if (has_pending) {
+                const Ray ray = load_ray(a.q, pi);
+                if (pend0 != kNoSphere) exact_sphere<ANY>(s, ray, pend0, h, n_exact, nan_count);
+                if (pend1 != kNoSphere) exact_sphere<ANY>(s, ray, pend1, h, n_exact, nan_count);
+                pend0 = pend1 = kNoSphere;
+            }
+        }
     }
+
     unsigned long long ne = n_exact;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         ne += __shfl_xor_sync(0xffffffffu, ne, o);
         nan_count += __shfl_xor_sync(0xffffffffu, nan_count, o);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         if (ne) atomicAdd(&a.ctr->exact_tests, ne);
         if (nan_count) atomicAdd(&a.ctr->err_nan, (unsigned long long)nan_count);
     }

@@ -53,6 +53,7 @@ struct GridDev {            // see rg_grid.cuh
     const uint32_t *cell_start;   // [ncells + 1]
     const uint32_t *cell_items;   // sphere indices (into the sphere list), cell by cell
     const float4 *cell_cull4;     // the same spheres' FP32 cull records, in the same order
+    const float4 *cell_rec;       // [ncells][3]: cull record of item 0, of item 1, (idx0, idx1, overflow begin, end)
     uint32_t n_loose;             // spheres kept out of the grid (too large): brute-forced
     const uint32_t *loose;        // their sphere-list indices
     uint32_t enabled;
@@ -88,7 +89,8 @@ struct DCounters {
     unsigned long long err_nan, err_trans, err_aabb;
     unsigned int q_next;               // wavefront: children emitted into the next level
     unsigned int q_lit;                // wavefront: hits that need shadow rays
-    unsigned int pad[2];
+    unsigned int fetch;                // persistent trace kernels: next unclaimed ray of the queue
+    unsigned int pad;
 };
 
 }  // namespace rg

@@ -42,6 +42,7 @@ struct TraceArgs {
     uint8_t *out_lit;        // ANY: 1 = in light
     DCounters *ctr;
     int verify;              // RG_OPT_VERIFY_CULL
+    int g_refill, g_quorum, g_burst;   // persistent grid kernel tuning (rg_grid.cuh)
 };
 
 // Path queues are dense (seg_len = 0).  Shadow queues hold one segment per light so that

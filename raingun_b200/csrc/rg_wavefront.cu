@@ -255,8 +255,17 @@ template <bool ANY>
 static int launch_trace(rg_scene *sc, const TraceArgs &ta, bool use_grid, cudaStream_t stream) {
     if (ta.n == 0) return RG_OK;
     if (use_grid) {
-        const unsigned blocks = (ta.n + kGridTraceThreads - 1) / kGridTraceThreads;
-        k_trace_grid<ANY><<<blocks, kGridTraceThreads, 0, stream>>>(sc->ds, ta);
+        // persistent warps: enough blocks to fill the chip, each pulling rays from ctr->fetch
+        const unsigned want = (ta.n + kGridTraceThreads - 1) / kGridTraceThreads;
+        static const int bps = [] { const char *e = getenv("RG_GRID_BPS"); return e ? atoi(e) : 6; }();
+        static const int t_refill = [] { const char *e = getenv("RG_GRID_REFILL"); return e ? atoi(e) : kGridRefill; }();
+        static const int t_quorum = [] { const char *e = getenv("RG_GRID_QUORUM"); return e ? atoi(e) : kGridExactQuorum; }();
+        static const int t_burst = [] { const char *e = getenv("RG_GRID_BURST"); return e ? atoi(e) : kGridScanBurst; }();
+        const unsigned blocks = std::min<unsigned>(want, (unsigned)(sc->sm_count * bps));
+        TraceArgs tuned = ta;
+        tuned.g_refill = t_refill; tuned.g_quorum = t_quorum; tuned.g_burst = t_burst;
+        RG_CUDA(cudaMemsetAsync(&ta.ctr->fetch, 0, sizeof(unsigned int), stream));
+        k_trace_grid<ANY><<<blocks, kGridTraceThreads, 0, stream>>>(sc->ds, tuned);
     } else {
         // register tiling R: 4 rays per thread when there is enough work to fill the chip
         const uint64_t full = (uint64_t)sc->sm_count * 2 * kTraceThreads;
