@@ -197,6 +197,17 @@ __device__ __forceinline__ C3 body_color(const DScene &s, uint32_t body, float u
     return c3((float)p.x / 255.0f, (float)p.y / 255.0f, (float)p.z / 255.0f);
 }
 
+// body.color(&body.texture_coords(&hit_point)) (rendering.rs:137-138, :98).  Coloration::Color
+// ignores the coordinates (material.rs:84-85), so they — and the atan2/acos behind the sphere's —
+// are only evaluated for textured bodies; the colour returned is the same either way.
+__device__ __forceinline__ C3 body_color_at(const DScene &s, uint32_t body, D3 hp) {
+    const BodyMat &m = s.mat[body];
+    if (m.coloration == RG_COLORATION_COLOR) return c3(m.color[0], m.color[1], m.color[2]);
+    float u, v;
+    texture_coords(s, body, hp, u, v);
+    return body_color(s, body, u, v);
+}
+
 // ---- lights (lights.rs:28-58) -------------------------------------------------------------
 __device__ __forceinline__ D3 light_direction_from(const DLight &l, D3 p) {
     if (l.kind == RG_LIGHT_DIRECTIONAL) return d3(l.v[0], l.v[1], l.v[2]);   // hoisted normalize(-direction)

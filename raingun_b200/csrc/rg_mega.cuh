@@ -19,9 +19,7 @@ struct MegaFrame {
 // rendering.rs:132-172 with a full nearest-hit trace per light, exactly as written there.
 __device__ __forceinline__ C3 mega_shade_diffuse(const DScene &s, uint32_t body, D3 hp, D3 n,
                                                  DCounters *ctr, unsigned long long &n_shadow) {
-    float u, v;
-    texture_coords(s, body, hp, u, v);
-    C3 bc = body_color(s, body, u, v);
+    C3 bc = body_color_at(s, body, hp);
     float albedo = s.mat[body].albedo;
     C3 fin = c3(0.0f, 0.0f, 0.0f);
     for (uint32_t l = 0; l < s.n_lights; ++l) {
@@ -84,9 +82,7 @@ k_render_mega(DScene s, uint32_t width, uint32_t height, uint32_t y0, uint32_t y
                     float kr = (float)fresnel(ray.d, n, m.p0);
                     f.p0 = kr;
                     f.p1 = m.p1;
-                    float u, v;
-                    texture_coords(s, h.body, hp, u, v);
-                    f.a = body_color(s, h.body, u, v);
+                    f.a = body_color_at(s, h.body, hp);
                     f.pending = create_reflection(n, ray.d, hp);
                     f.b = dflt;
                     f.stage = 1;

@@ -71,9 +71,7 @@ __global__ void __launch_bounds__(256) k_shade(const DScene s, const LevelBuffer
             hp = ray.o + ray.d * lb.hit_t[i];                       // rendering.rs:81
             n = surface_normal(s, body, hp, ctr);                  // :83
             const BodyMat &m = s.mat[body];
-            float u, v;
-            texture_coords(s, body, hp, u, v);
-            bc = body_color(s, body, u, v);
+            bc = body_color_at(s, body, hp);
             if (m.surface == RG_SURFACE_REFRACTIVE) {              // :95-117
                 kind = NODE_REFRACTIVE;
                 float kr = (float)fresnel(ray.d, n, m.p0);
@@ -98,19 +96,34 @@ __global__ void __launch_bounds__(256) k_shade(const DScene s, const LevelBuffer
             }
         }
     }
-    // ---- queue compaction: one atomic per warp per queue, slots by ballot + popc
+    // ---- queue compaction: slots by warp ballot + popc, warps ranked inside the block through
+    // shared-memory counters, ONE global atomic per block per queue (the per-warp version spent
+    // half of this kernel serialised on three L2 addresses).
+    __shared__ uint32_t sh_cnt[3];     // lit, reflection, transmission entries of this block
+    __shared__ uint32_t sh_base[2];    // block base in the lit / next-level queues
+    if (threadIdx.x < 3) sh_cnt[threadIdx.x] = 0;
+    __syncthreads();
     const uint32_t m_lit = __ballot_sync(0xffffffffu, want_lit);
     const uint32_t m_refl = __ballot_sync(0xffffffffu, want_refl);
     const uint32_t m_trans = __ballot_sync(0xffffffffu, want_trans);
-    uint32_t base_lit = 0, base_next = 0;
+    uint32_t w_lit = 0, w_next = 0;
     if (lane == 0) {
-        if (m_lit) base_lit = atomicAdd(&ctr->q_lit, (unsigned)__popc(m_lit));
-        if (m_refl | m_trans) base_next = atomicAdd(&ctr->q_next, (unsigned)(__popc(m_refl) + __popc(m_trans)));
-        if (m_refl) atomicAdd(&ctr->rays[2], (unsigned long long)__popc(m_refl));
-        if (m_trans) atomicAdd(&ctr->rays[3], (unsigned long long)__popc(m_trans));
+        if (m_lit) w_lit = atomicAdd(&sh_cnt[0], (unsigned)__popc(m_lit));
+        // a warp's children are laid out [reflections..., transmissions...]; the block interleaves warps
+        if (m_refl | m_trans) w_next = atomicAdd(&sh_cnt[1], (unsigned)(__popc(m_refl) + __popc(m_trans)));
+        if (m_trans) atomicAdd(&sh_cnt[2], (unsigned)__popc(m_trans));
     }
-    base_lit = __shfl_sync(0xffffffffu, base_lit, 0);
-    base_next = __shfl_sync(0xffffffffu, base_next, 0);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t n_lit_b = sh_cnt[0], n_next_b = sh_cnt[1], n_trans_b = sh_cnt[2];
+        sh_base[0] = n_lit_b ? atomicAdd(&ctr->q_lit, n_lit_b) : 0u;
+        sh_base[1] = n_next_b ? atomicAdd(&ctr->q_next, n_next_b) : 0u;
+        if (n_next_b - n_trans_b) atomicAdd(&ctr->rays[2], (unsigned long long)(n_next_b - n_trans_b));
+        if (n_trans_b) atomicAdd(&ctr->rays[3], (unsigned long long)n_trans_b);
+    }
+    __syncthreads();
+    const uint32_t base_lit = sh_base[0] + __shfl_sync(0xffffffffu, w_lit, 0);
+    const uint32_t base_next = sh_base[1] + __shfl_sync(0xffffffffu, w_next, 0);
     uint32_t child_refl = kChildDefault, child_trans = kChildDefault;
     if (want_refl) {
         child_refl = base_next + __popc(m_refl & lt);
