@@ -57,6 +57,21 @@ def static_chunk(num_tiles: int, world: int, rank: int) -> List[int]:
     return list(range(rank, num_tiles, world))
 
 
+def hybrid_plan(num_tiles: int, world: int, tail_every: int = 4, min_chunk: int = 2):
+    """Work stealing without paying for it when the load is balanced: 1 - 1/tail_every of the
+    tiles are owned statically (interleaved over the image and over the ranks: one large batch per
+    rank, no counter traffic); every ``tail_every``-th tile forms the tail that is handed out by
+    the work-stealing counter in guided chunks, which absorbs whatever imbalance remains.
+    Returns ``(static_tiles_per_rank, tail_chunks)``."""
+    if world <= 1 or num_tiles < 4 * world:
+        return [list(range(num_tiles))] + [[] for _ in range(max(world, 1) - 1)], []
+    static = [t for t in range(num_tiles) if t % tail_every != tail_every - 1]
+    tail = [t for t in range(num_tiles) if t % tail_every == tail_every - 1]
+    per_rank = [static[r::world] for r in range(world)]
+    chunks = [[tail[i] for i in c] for c in guided_chunks(len(tail), world, min_chunk)]
+    return per_rank, chunks
+
+
 class TileCounter:
     """Work-stealing counter over a c10d store: ``store.add`` is an atomic fetch-add."""
 
@@ -88,8 +103,9 @@ def render_frame_sharded(render_rowlist: Callable[[np.ndarray, torch.Tensor], ob
 
     ``render_rowlist(rows, out)`` must fill ``out`` (a uint8 tensor of ``len(rows)*width*4``
     bytes on ``device``) with the listed image rows, compacted in list order — on a GPU that is
-    ``Scene.render_rowlist_device``.  ``schedule`` is ``"steal"`` (work-stealing counter) or
-    ``"static"`` (interleaved ownership, one batch per rank).
+    ``Scene.render_rowlist_device``.  ``schedule`` is ``"steal"`` (static interleaved share first, then the
+    work-stealing counter for the tail — see ``hybrid_plan``) or ``"static"`` (interleaved
+    ownership only, one batch per rank).
     """
     nt = n_tiles(height, tile_rows)
     res = ShardResult(frame=None)
@@ -102,7 +118,13 @@ def render_frame_sharded(render_rowlist: Callable[[np.ndarray, torch.Tensor], ob
     elif schedule == "steal":
         if store is None:
             store = default_store()
-        claim = TileCounter(store, f"raingun/tiles/{frame_id}", guided_chunks(nt, world)).claim
+        per_rank, tail_chunks = hybrid_plan(nt, world)
+        counter = TileCounter(store, f"raingun/tiles/{frame_id}", tail_chunks)
+        own = iter([per_rank[rank]] if per_rank[rank] else [])
+
+        def claim():
+            mine = next(own, None)
+            return mine if mine is not None else counter.claim()
     elif schedule == "static":
         pending = iter([static_chunk(nt, world, rank)])
         claim = lambda: next(pending, None)

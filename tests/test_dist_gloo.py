@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from raingun_b200.dist import guided_chunks, n_tiles, render_frame_sharded, rows_of_tiles, static_chunk
+from raingun_b200.dist import guided_chunks, hybrid_plan, n_tiles, render_frame_sharded, rows_of_tiles, static_chunk
 
 W, H, TILE = 96, 54, 4
 
@@ -73,5 +73,8 @@ def test_schedules_cover_every_tile_once():
             assert [t for c in chunks for t in c] == list(range(nt))
             assert all(len(a) >= len(b) for a, b in zip(chunks, chunks[1:]))          # large first, small last
             assert sorted(t for r in range(world) for t in static_chunk(nt, world, r)) == list(range(nt))
+            per_rank, tail = hybrid_plan(nt, world)
+            covered = sorted([t for r in per_rank for t in r] + [t for c in tail for t in c])
+            assert covered == list(range(nt)) and len(per_rank) == max(world, 1)
     assert rows_of_tiles([0, 13], 4, 54).tolist() == [0, 1, 2, 3, 52, 53]             # ragged last tile
     assert rows_of_tiles([], 4, 54).size == 0
