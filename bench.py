@@ -159,6 +159,7 @@ def main() -> int:
     ap.add_argument("--accel", default="auto", choices=["auto", "grid", "brute"])
     ap.add_argument("--schedule", default="steal", choices=["steal", "static"])
     ap.add_argument("--tile-rows", type=int, default=8)
+    ap.add_argument("--gather", default="reduce", choices=["reduce", "p2p"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget (N=1)")
     ap.add_argument("--reference-budget", type=float, default=150.0, help="--impl reference: total seconds")
     ap.add_argument("--no-roofline", action="store_true")
@@ -220,6 +221,7 @@ def main() -> int:
     scene = rg.Scene(data, device=local_rank)
     scene.set_accel(accel)
     staging = torch.empty((h * w * 4,), dtype=torch.uint8, device=device)
+    frame_buf = torch.empty((h, w, 4), dtype=torch.uint8, device=device) if world > 1 else None
     host_frame = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()
     frame_counter = [0]
 
@@ -233,7 +235,8 @@ def main() -> int:
         frame_counter[0] += 1
         res = render_frame_sharded(
             lambda rows, out: sc.render_rowlist_device(w, h, rows, out.data_ptr(), sptr), w, h, rank, world,
-            frame_counter[0], device, tile_rows=args.tile_rows, schedule=args.schedule, staging=staging)
+            frame_counter[0], device, tile_rows=args.tile_rows, schedule=args.schedule, staging=staging,
+            gather_mode=args.gather, frame_buf=frame_buf)
         gathered["frame"] = res.frame   # rank 0: the gathered (H, W, 4) frame in HBM
         return (sum(s.rays for s in res.stats), sum(s.gpu_launches for s in res.stats),
                 res.stats[-1] if res.stats else None)
@@ -350,7 +353,7 @@ def main() -> int:
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.workload, spec, data, {
                 "accel": accel_used, "pipeline": "wavefront",
-                "parallelism": f"row-tiles x{world} ({args.schedule}, {args.tile_rows}-row tiles)" if world > 1 else "1 GPU",
+                "parallelism": f"row-tiles x{world} ({args.schedule}, {args.tile_rows}-row tiles, gather={args.gather})" if world > 1 else "1 GPU",
                 "l2": "per-frame working set (ray queues + nodes, several GB) exceeds the 126 MB L2; no explicit flush"}),
             "rays_per_frame": rays // max(1, args.steps),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": desc_bytes * world,

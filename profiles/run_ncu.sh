@@ -12,11 +12,19 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
     --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launch_${TAG}.log 2>&1
 echo "launch list rc=$?"
 $CMD > /dev/null 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_trace_grid -s 2 -c 3 \
+ncu --set full --clock-control none --import-source on -k regex:k_trace_grid -s 18 -c 2 \
     -o gpurun_out/prof_grid_${TAG} -f $CMD > gpurun_out/ncu_grid_${TAG}.log 2>&1
 echo "grid capture rc=$?"
 $CMD > /dev/null 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_trace_brute -s 0 -c 2 \
     -o gpurun_out/prof_brute_${TAG} -f $CMD > gpurun_out/ncu_brute_${TAG}.log 2>&1
 echo "brute capture rc=$?"
+$CMD > /dev/null 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_trace_brute -s 14 -c 2 \
+    -o gpurun_out/prof_brute_deep_${TAG} -f $CMD > gpurun_out/ncu_brute_deep_${TAG}.log 2>&1
+echo "deep brute capture rc=$?"
+$CMD > /dev/null 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_shade -s 9 -c 1 \
+    -o gpurun_out/prof_shade_${TAG} -f $CMD > gpurun_out/ncu_shade_${TAG}.log 2>&1
+echo "shade capture rc=$?"
 ls -la gpurun_out/

@@ -2,6 +2,7 @@
 // error reporting.  Host-side hoists are limited to values that are pure functions of the
 // scene and are computed with the reference's own operation order (this file is compiled
 // with -ffp-contract=off on the host side).
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <cmath>
@@ -61,22 +62,54 @@ void WavefrontScratch::release() {
     s_tmax.release(); s_ab.release(); s_lit.release(); lit_bc.release(); lit_node.release();
     for (auto &b : nodes) b.release();
     nodes.clear();
+    for (auto e : events) cudaEventDestroy(e);
+    events.clear();
 }
 
 // Scratch arenas outlive a scene: destroying a scene parks its (possibly multi-GB) wavefront
 // buffers here and the next scene created on the same device adopts them, so a host that
 // re-uploads the scene every frame does not pay cudaMalloc/cudaFree for them each time.
-struct ParkedScratch { bool used = false; WavefrontScratch wf; DeviceBuffer frame; };
+struct ParkedContext {
+    bool used = false;
+    WavefrontScratch wf;
+    DeviceBuffer frame, rowlist;
+    SceneArena arena;
+    DCounters *d_counters = nullptr, *h_counters = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
 static std::mutex g_park_mutex;
-static std::map<int, ParkedScratch> g_parked;
+static std::map<int, ParkedContext> g_parked;
+
+void *SceneArena::alloc(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    for (;;) {
+        if (cur < blocks.size() && off + bytes <= blocks[cur].cap) {
+            void *p = static_cast<char *>(blocks[cur].ptr) + off;
+            off += bytes;
+            return p;
+        }
+        if (cur + 1 < blocks.size()) { ++cur; off = 0; continue; }
+        DeviceBuffer b;
+        if (b.reserve(std::max<size_t>(bytes, (size_t)16 << 20)) != RG_OK) return nullptr;
+        blocks.push_back(b);
+        cur = blocks.size() - 1;
+        off = 0;
+    }
+}
+void SceneArena::release() {
+    for (auto &b : blocks) b.release();
+    blocks.clear();
+    reset();
+}
 
 template <typename T>
 static int upload(rg_scene *sc, const T *host, size_t count, const T **out) {
     *out = nullptr;
     if (count == 0) return RG_OK;
-    void *p = nullptr;
-    RG_CUDA(cudaMalloc(&p, count * sizeof(T)));
-    sc->owned.push_back(p);
+    void *p = sc->arena.alloc(count * sizeof(T));
+    if (!p) return RG_E_NOMEM;
     RG_CUDA(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
     *out = reinterpret_cast<const T *>(p);
     return RG_OK;
@@ -317,18 +350,25 @@ void rg_scene_destroy(rg_scene *sc) {
     cudaSetDevice(sc->device);
     for (auto o : sc->tex_objs) cudaDestroyTextureObject(o);
     for (auto a : sc->tex_arrays) cudaFreeArray(a);
-    for (auto p : sc->owned) cudaFree(p);
     {
         std::lock_guard<std::mutex> lock(g_park_mutex);
-        ParkedScratch &slot = g_parked[sc->device];
-        if (!slot.used) {
+        ParkedContext &slot = g_parked[sc->device];
+        if (!slot.used && sc->stream) {   // park the device-side context for the next scene on this device
+            if (sc->h_frame) cudaFreeHost(sc->h_frame);
             slot.used = true;
             slot.wf = std::move(sc->wf);
             slot.frame = sc->frame;
-            sc->wf = WavefrontScratch{};
-            sc->frame = DeviceBuffer{};
+            slot.rowlist = sc->rowlist;
+            slot.arena = std::move(sc->arena);
+            slot.d_counters = sc->d_counters;
+            slot.h_counters = sc->h_counters;
+            slot.stream = sc->stream;
+            for (int k = 0; k < 4; ++k) slot.ev[k] = sc->ev[k];
+            delete sc;
+            return;
         }
     }
+    sc->arena.release();
     sc->wf.release();
     sc->frame.release();
     sc->rowlist.release();
@@ -364,22 +404,32 @@ int rg_scene_create(const rg_scene_desc *desc, int32_t device, rg_scene **out) {
     sc->device = device;
     sc->sm_count = prop.multiProcessorCount;
     auto fail = [&](int code) { rg_scene_destroy(sc); return code; };
-    if (cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "stream", __FILE__, __LINE__));
-    for (auto &ev : sc->ev)
-        if (cudaEventCreate(&ev) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__));
-    if (cudaMalloc(&sc->d_counters, sizeof(DCounters)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "counters", __FILE__, __LINE__));
-    if (cudaMallocHost(&sc->h_counters, sizeof(DCounters)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "counters", __FILE__, __LINE__));
-    rc = build_scene(sc, desc);
-    if (rc) return fail(rc);
     {
         std::lock_guard<std::mutex> lock(g_park_mutex);
         auto it = g_parked.find(device);
-        if (it != g_parked.end() && it->second.used) {
-            sc->wf = std::move(it->second.wf);
-            sc->frame = it->second.frame;
-            it->second = ParkedScratch{};
+        if (it != g_parked.end() && it->second.used) {   // adopt the context the last scene left behind
+            ParkedContext &slot = it->second;
+            sc->wf = std::move(slot.wf);
+            sc->frame = slot.frame;
+            sc->rowlist = slot.rowlist;
+            sc->arena = std::move(slot.arena);
+            sc->arena.reset();
+            sc->d_counters = slot.d_counters;
+            sc->h_counters = slot.h_counters;
+            sc->stream = slot.stream;
+            for (int k = 0; k < 4; ++k) sc->ev[k] = slot.ev[k];
+            slot = ParkedContext{};
         }
     }
+    if (!sc->stream) {
+        if (cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "stream", __FILE__, __LINE__));
+        for (auto &ev : sc->ev)
+            if (cudaEventCreate(&ev) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__));
+        if (cudaMalloc(&sc->d_counters, sizeof(DCounters)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "counters", __FILE__, __LINE__));
+        if (cudaMallocHost(&sc->h_counters, sizeof(DCounters)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "counters", __FILE__, __LINE__));
+    }
+    rc = build_scene(sc, desc);
+    if (rc) return fail(rc);
     *out = sc;
     return RG_OK;
 }

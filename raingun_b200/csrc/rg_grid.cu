@@ -13,9 +13,8 @@ template <typename T>
 static int upload_vec(rg_scene *sc, const std::vector<T> &v, const T **out) {
     *out = nullptr;
     if (v.empty()) return RG_OK;
-    void *p = nullptr;
-    RG_CUDA(cudaMalloc(&p, v.size() * sizeof(T)));
-    sc->owned.push_back(p);
+    void *p = sc->arena.alloc(v.size() * sizeof(T));
+    if (!p) return RG_E_NOMEM;
     RG_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     *out = reinterpret_cast<const T *>(p);
     return RG_OK;

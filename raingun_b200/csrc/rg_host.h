@@ -30,6 +30,17 @@ struct DeviceBuffer {
     template <typename T> T *as() const { return reinterpret_cast<T *>(ptr); }
 };
 
+// Scene arrays are carved out of a few large blocks instead of one cudaMalloc each, and the
+// blocks survive the scene (see ParkedContext in rg_api.cu): re-uploading a scene every frame
+// then costs H2D copies only.
+struct SceneArena {
+    std::vector<DeviceBuffer> blocks;
+    size_t cur = 0, off = 0;
+    void *alloc(size_t bytes);   // nullptr on failure (error already set)
+    void reset() { cur = 0; off = 0; }
+    void release();
+};
+
 // Scratch of the wavefront pipeline (rg_wavefront.cu).
 struct WavefrontScratch {
     DeviceBuffer ray[2];        // ping-pong path-ray queues: 3 x double2 per ray
@@ -41,6 +52,7 @@ struct WavefrontScratch {
     DeviceBuffer lit_bc;        // float4 (body colour, albedo) per lit hit
     DeviceBuffer lit_node;      // node index per lit hit
     std::vector<DeviceBuffer> nodes;   // per level: NodeA float4 + NodeB uint4
+    std::vector<cudaEvent_t> events;   // timing events of the trace launches, reused across frames
     void release();
 };
 
@@ -49,7 +61,7 @@ struct WavefrontScratch {
 struct rg_scene {
     int device = 0;
     rg::DScene ds{};                    // device pointers inside
-    std::vector<void *> owned;          // cudaMalloc'd scene arrays
+    rg::SceneArena arena;               // scene arrays
     std::vector<cudaArray_t> tex_arrays;
     std::vector<cudaTextureObject_t> tex_objs;
     rg::DCounters *d_counters = nullptr;

@@ -251,8 +251,9 @@ static RayQueue make_queue(DeviceBuffer &b, size_t cap) {
 }
 
 struct EventPool {
-    std::vector<cudaEvent_t> ev;
+    std::vector<cudaEvent_t> &ev;   // owned by the scratch (kept across frames)
     size_t used = 0;
+    explicit EventPool(std::vector<cudaEvent_t> &store) : ev(store) {}
     cudaEvent_t get() {
         if (used == ev.size()) {
             cudaEvent_t e;
@@ -261,7 +262,6 @@ struct EventPool {
         }
         return ev[used++];
     }
-    ~EventPool() { for (auto e : ev) cudaEventDestroy(e); }
 };
 
 template <bool ANY>
@@ -450,7 +450,7 @@ int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0,
     else if (sc->accel == RG_ACCEL_AUTO) use_grid = ds.grid.enabled != 0 && ds.n_spheres >= 64;
     st->accel_used = use_grid ? RG_ACCEL_GRID : RG_ACCEL_BRUTE;
 
-    EventPool events;
+    EventPool events(sc->wf.events);
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_spans;
     const uint32_t rows = y1 - y0;
     const uint64_t batch_pixels = sc->batch_pixels ? sc->batch_pixels : (16ull << 20);

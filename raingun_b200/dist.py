@@ -57,7 +57,7 @@ def static_chunk(num_tiles: int, world: int, rank: int) -> List[int]:
     return list(range(rank, num_tiles, world))
 
 
-def hybrid_plan(num_tiles: int, world: int, tail_every: int = 4, min_chunk: int = 2):
+def hybrid_plan(num_tiles: int, world: int, tail_every: int = 16, min_chunk: int = 2):
     """Work stealing without paying for it when the load is balanced: 1 - 1/tail_every of the
     tiles are owned statically (interleaved over the image and over the ranks: one large batch per
     rank, no counter traffic); every ``tail_every``-th tile forms the tail that is handed out by
@@ -68,7 +68,9 @@ def hybrid_plan(num_tiles: int, world: int, tail_every: int = 4, min_chunk: int 
     static = [t for t in range(num_tiles) if t % tail_every != tail_every - 1]
     tail = [t for t in range(num_tiles) if t % tail_every == tail_every - 1]
     per_rank = [static[r::world] for r in range(world)]
-    chunks = [[tail[i] for i in c] for c in guided_chunks(len(tail), world, min_chunk)]
+    # one tail chunk per rank on average: a claim is a whole wavefront batch (~1 ms of fixed cost)
+    per = max(min_chunk, (len(tail) + world - 1) // world)
+    chunks = [tail[i:i + per] for i in range(0, len(tail), per)]
     return per_rank, chunks
 
 
@@ -98,7 +100,8 @@ def default_store():
 def render_frame_sharded(render_rowlist: Callable[[np.ndarray, torch.Tensor], object], width: int, height: int,
                          rank: int, world: int, frame_id: int, device: torch.device, store=None,
                          tile_rows: int = DEFAULT_TILE_ROWS, schedule: str = "steal",
-                         gather: bool = True, staging: Optional[torch.Tensor] = None) -> ShardResult:
+                         gather: bool = True, staging: Optional[torch.Tensor] = None,
+                         gather_mode: str = "reduce", frame_buf: Optional[torch.Tensor] = None) -> ShardResult:
     """Renders one frame across ``world`` ranks.
 
     ``render_rowlist(rows, out)`` must fill ``out`` (a uint8 tensor of ``len(rows)*width*4``
@@ -106,6 +109,11 @@ def render_frame_sharded(render_rowlist: Callable[[np.ndarray, torch.Tensor], ob
     ``Scene.render_rowlist_device``.  ``schedule`` is ``"steal"`` (static interleaved share first, then the
     work-stealing counter for the tail — see ``hybrid_plan``) or ``"static"`` (interleaved
     ownership only, one batch per rank).
+
+    ``gather_mode``: ``"reduce"`` — every rank scatters its rows into a zeroed full frame and ONE
+    NCCL reduce (MAX over disjoint rows, i.e. a gather that needs no ownership exchange) lands the
+    frame on rank 0 over NVLink; ``"p2p"`` — the row lists travel through the store and rank 0
+    receives each rank's packed rows point to point.
     """
     nt = n_tiles(height, tile_rows)
     res = ShardResult(frame=None)
@@ -155,6 +163,13 @@ def render_frame_sharded(render_rowlist: Callable[[np.ndarray, torch.Tensor], ob
     if world == 1:
         res.frame = packed.view(height, width, 4) if np.array_equal(rows_all, np.arange(height)) else \
             _scatter_rows(torch.empty((height, width, 4), dtype=torch.uint8, device=device), rows_all, packed, width)
+        return res
+    if gather_mode == "reduce":
+        frame = frame_buf if frame_buf is not None else torch.empty((height, width, 4), dtype=torch.uint8, device=device)
+        frame.zero_()
+        _scatter_rows(frame, rows_all, packed, width)
+        dist.reduce(frame, dst=0, op=dist.ReduceOp.MAX)
+        res.frame = frame if rank == 0 else None
         return res
     if store is None:
         store = default_store()

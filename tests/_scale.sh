@@ -1,0 +1,17 @@
+#!/bin/bash
+# scaling sweep on one box: bash tests/_scale.sh "1 2 4 8"
+for n in $1; do
+  if [ "$n" = "1" ]; then
+    python bench.py --gpus 1 --steps 8 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/scale_$n.json 2> gpurun_out/scale_$n.err
+  else
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600+n)) bench.py --gpus $n --steps 8 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/scale_$n.json 2> gpurun_out/scale_$n.err
+  fi
+  python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/scale_$n.json").read().strip().splitlines()[-1])
+    print("N=$n value %.1f Mrays/s  %.2f ms/frame | e2e %.1f Mrays/s %.2f ms | launches %d | %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["e2e"]["ms_per_step"], d["gpu_launches"], d["config"]["parallelism"]))
+except Exception as e:
+    print("N=$n ERR", e); print(open("gpurun_out/scale_$n.err").read()[-1500:])
+PY
+done

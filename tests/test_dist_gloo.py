@@ -21,7 +21,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, schedule, out_dir):
+def _worker(rank, world, port, schedule, out_dir, gather_mode="p2p"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import oracle
@@ -41,7 +41,7 @@ def _worker(rank, world, port, schedule, out_dir):
     tiles = []
     for frame_id in (1, 2):   # two frames: the counter keys must not collide
         res = render_frame_sharded(render_rowlist, W, H, rank, world, frame_id, torch.device("cpu"),
-                                   tile_rows=TILE, schedule=schedule)
+                                   tile_rows=TILE, schedule=schedule, gather_mode=gather_mode)
         tiles.append(sorted(res.my_tiles))
         if rank == 0:
             np.save(os.path.join(out_dir, f"frame{frame_id}.npy"), res.frame.numpy())
@@ -50,10 +50,10 @@ def _worker(rank, world, port, schedule, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("schedule", ["steal", "static"])
-def test_two_ranks_reassemble_the_frame(tmp_path, oracle, schedule):
+@pytest.mark.parametrize("schedule,gather_mode", [("steal", "p2p"), ("static", "p2p"), ("steal", "reduce")])
+def test_two_ranks_reassemble_the_frame(tmp_path, oracle, schedule, gather_mode):
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), schedule, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), schedule, str(tmp_path), gather_mode), nprocs=world, join=True)
     from raingun_b200.synth import make_scene
 
     data, _ = make_scene("C4", spheres=40, depth=4)
