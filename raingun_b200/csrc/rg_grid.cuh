@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
     int cell = 0, scx = 0, scy = 0, scz = 0;                   // linear cell index and its per-axis stride (signed)
     uint32_t pend0 = kNoSphere, pend1 = kNoSphere;             // cull survivors waiting for their exact test
     bool fresh = false;                                        // the current cell's record has not been examined yet
+    uint32_t ok = 0, oe = 0;                                   // cursor / end of the current cell's overflow list
     float4 c0, c1, n0, n1;                                     // cull records of the current / prefetched next cell
     uint4 cm, nm;                                              // ... and their (idx0, idx1, overflow begin, end)
     bool exhausted = false;                                    // warp-uniform: the queue has no more rays
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
                 walking = false;
                 pend0 = pend1 = kNoSphere;
                 fresh = false;
+                ok = oe = 0;
                 pi = phys_index(a, ri);
                 const Ray ray = load_ray(a.q, pi);
                 h.best.init();
@@ -270,17 +272,19 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
             const bool go = active && pend0 == kNoSphere && pend1 == kNoSphere;
             if (go && walking) {
                 if (fresh) {
-                    // examine the current cell: two inline items, rarely an overflow list
+                    // examine the current cell: its two inline items now, an overflow list (cells with
+                    // more than two items, ~4 %) two items per step below
                     if (cm.x != kNoSphere && !cull_reject(cr, c0)) pend0 = cm.x;
                     if (cm.y != kNoSphere && !cull_reject(cr, c1)) pend1 = cm.y;
-                    if (cm.w) {   // > 2 items: the rest of the list, exact tests inline (rare)
-                        const Ray ray = load_ray(a.q, pi);
-                        for (uint32_t q = cm.z; q < cm.w; ++q)
-                            if (!cull_reject(cr, g.cell_cull4[q])) exact_sphere<ANY>(s, ray, g.cell_items[q], h, n_exact, nan_count);
-                    }
+                    ok = cm.z;
+                    oe = cm.w;
                     fresh = false;
+                } else if (ok < oe) {
+                    if (!cull_reject(cr, g.cell_cull4[ok])) pend0 = g.cell_items[ok];
+                    if (ok + 1 < oe && !cull_reject(cr, g.cell_cull4[ok + 1])) pend1 = g.cell_items[ok + 1];
+                    ok += 2;
                 }
-                if (pend0 == kNoSphere && pend1 == kNoSphere) {
+                if (pend0 == kNoSphere && pend1 == kNoSphere && ok >= oe) {
                     // every item of the current cell is decided: stop, or step to the next cell
                     // (branch-free axis choice; its record was prefetched)
                     const float tnext = fminf(tnx, fminf(tny, tnz));
