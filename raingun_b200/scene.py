@@ -254,11 +254,11 @@ def _need(d: Any, key: str, what: str):
 
 
 def default_texture_loader(path: str) -> np.ndarray:
-    """material.rs:34-47 (`image::open`), decoded with Pillow; RGB8."""
-    from PIL import Image
+    """material.rs:34-47 (`image::open`), decoded by the native host library
+    (host/rgh_jpeg.cpp restates jpeg-decoder 0.1.11; host/rgh_png.cpp); RGB8 or RGBA8."""
+    from . import host
 
-    with Image.open(path) as im:
-        return np.asarray(im.convert("RGB"), dtype=np.uint8).copy()
+    return host.open_image(path)
 
 
 def scene_from_dict(doc: Any, texture_loader: Callable[[str], np.ndarray] = default_texture_loader

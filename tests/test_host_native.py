@@ -1,0 +1,282 @@
+"""The native host library (include/raingun_host.h, raingun_b200/host/): C++ YAML scene loader,
+JPEG / PNG codecs and CLI option mapping — SURVEY.md section 8(f) row 3.  CPU-only."""
+import ctypes
+import io
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from raingun_b200 import host
+from raingun_b200 import scene as pyscene
+from raingun_b200.examples import _bundle, bundled_texture_loader, example_yaml
+from raingun_b200.synth import make_scene, make_scene_doc, to_yaml
+
+FIELDS = ("body_kind", "body_geom", "coloration_kind", "color", "texture_id", "texture_offset", "albedo",
+          "surface_kind", "surface_param", "light_kind", "light_vec", "light_color", "light_intensity")
+
+
+def assert_same_scene(a, b):
+    assert a.fov == b.fov and a.max_recursion_depth == b.max_recursion_depth
+    assert np.array_equal(np.asarray(a.default_color, np.float32), np.asarray(b.default_color, np.float32))
+    for f in FIELDS:
+        x, y = getattr(a, f), getattr(b, f)
+        assert x.dtype == y.dtype and x.shape == y.shape, f
+        assert x.tobytes() == y.tobytes(), f  # bit-equal, NaN-safe
+    assert a.texture_names == b.texture_names
+    assert len(a.textures) == len(b.textures)
+    for x, y in zip(a.textures, b.textures):
+        assert np.array_equal(x, y)
+
+
+def test_library_exports_every_declared_symbol():
+    L = host.lib()
+    hdr = open(os.path.join(os.path.dirname(host.LIB_PATH), "..", "include", "raingun_host.h")).read()
+    import re
+    declared = set(re.findall(r"\b(rgh_[a-z0-9_]+)\s*\(", hdr)) - {"rgh_texture_cb"}
+    assert declared == set(host.EXPORTS)
+    for name in host.EXPORTS:
+        assert hasattr(L, name), name
+
+
+# ------------------------------------------------------------------------------------ YAML / schema
+@pytest.mark.parametrize("name", ["test1", "test2", "test3"])
+def test_native_loader_equals_python_loader_on_examples(name):
+    text = example_yaml(name)
+    assert_same_scene(host.parse_scene(text, bundled_texture_loader), pyscene.parse_scene(text, bundled_texture_loader))
+
+
+@pytest.mark.parametrize("cfg,spheres", [("C3", 200), ("C4", 500), ("C5", 300)])
+def test_native_loader_equals_python_loader_on_synthetic_yaml(cfg, spheres):
+    data, spec = make_scene(cfg, spheres=spheres, texture_loader=bundled_texture_loader)
+    text = to_yaml(make_scene_doc(spec, spheres))  # what the reference CLI would be given
+    native = host.parse_scene(text, bundled_texture_loader)
+    assert_same_scene(native, data)
+    assert native.n_bodies == spheres + 1
+
+
+def test_yaml_forms_the_reference_schema_allows():
+    text = """
+# comment line
+fov: 60   # integer where f64 is expected
+maxRecursionDepth: 3
+defaultColor: '#102030'
+lights:
+- Spherical: {position: {x: 1, y: 2.5, z: -3e0}, color: "#ffffff", intensity: 1e3}
+- Directional:
+    direction: [0.0, -1.0,
+                0.0]
+    color: "#ff0000"
+    intensity: +2
+bodies:
+  - Disk:
+      origin: [0, 0, -5]
+      normal: {x: 0, y: 0, z: -1}
+      radius: 2
+      ignored_extra_key: 1      # only the root denies unknown fields (scene.rs:12)
+      material: {coloration: {Color: "#00ff00"}, albedo: 0.5, surface: Diffuse}
+  - AABB:
+      bounds: [[-1, -1, -6], {x: 1, y: 1, z: -4}]
+      material:
+        coloration: {Color: "#0000ff"}
+        albedo: .25
+        surface: {Refractive: {index: 1.33, transparency: 0.8}}
+  - Sphere:
+      center: [0, 0, -3]
+      radius: 1.
+      material:
+        coloration:
+          Color: "#+00aBc"
+        albedo: 1
+        surface:
+          Reflecting:
+            reflectivity: 0.75
+"""
+    sd = host.parse_scene(text)
+    assert sd.fov == 60.0 and sd.max_recursion_depth == 3
+    assert np.allclose(sd.default_color, np.array([0x10, 0x20, 0x30], np.float32) / np.float32(255))
+    assert list(sd.light_kind) == [pyscene.LIGHT_SPHERICAL, pyscene.LIGHT_DIRECTIONAL]
+    assert sd.light_vec.tolist() == [[1.0, 2.5, -3.0], [0.0, -1.0, 0.0]]
+    assert sd.light_intensity.tolist() == [1000.0, 2.0]
+    assert list(sd.body_kind) == [pyscene.BODY_DISK, pyscene.BODY_AABB, pyscene.BODY_SPHERE]
+    assert sd.body_geom[0].tolist() == [0, 0, -5, 0, 0, -1, 2, 0]
+    assert sd.body_geom[1].tolist() == [-1, -1, -6, 1, 1, -4, 0, 0]
+    assert sd.surface_param[1].tolist() == [float(np.float32(1.33)), float(np.float32(0.8))]  # f64 -> `as f32`
+    assert sd.albedo.tolist() == [0.5, 0.25, 1.0]
+    assert np.array_equal(sd.color[2], np.array([0x00, 0x0a, 0xbc], np.float32) / np.float32(255))
+    assert_same_scene(sd, pyscene.parse_scene(text.replace('"#+00aBc"', '"#000abc"').replace("intensity: +2", "intensity: 2")))
+
+
+def test_empty_document_is_the_default_scene():
+    for text in ("", "---\n", "# nothing\n"):
+        sd = host.parse_scene(text)
+        assert sd.fov == 90.0 and sd.max_recursion_depth == 10 and sd.n_bodies == 0 and sd.n_lights == 0
+        assert sd.default_color.tolist() == [0.0, 0.0, 0.0]
+
+
+@pytest.mark.parametrize("text,code,needle", [
+    ("fov: 90\nfoo: 1\n", host.E_SCHEMA, "unknown field `foo`"),                       # scene.rs:12
+    ("defaultColor: \"#12345\"\n", host.E_SCHEMA, "is not a valid color"),             # color.rs:129
+    ("defaultColor: \"#12345g\"\n", host.E_SCHEMA, "is not a valid color"),
+    ("defaultColor: 7\n", host.E_SCHEMA, "expected a string of a simple hex color"),   # color.rs:138
+    ("fov: \"90\"\n", host.E_SCHEMA, "expected f64"),                                  # quoted = string
+    ("maxRecursionDepth: -1\n", host.E_SCHEMA, "expected u32"),
+    ("bodies:\n  - Cube: {}\n", host.E_SCHEMA, "unknown variant `Cube`"),
+    ("bodies:\n  - Sphere:\n      center: [0, 0, -3]\n", host.E_SCHEMA, "missing field `radius`"),
+    ("bodies:\n  - Sphere:\n      center: [0, 0]\n      radius: 1\n", host.E_SCHEMA, "expected [x, y, z]"),
+    ("lights:\n  - Spherical: {position: [0,0,0], color: \"#ffffff\"}\n", host.E_SCHEMA, "missing field `intensity`"),
+    ("bodies:\n  - Sphere: {center: [0,0,0], radius: 1, material: {coloration: {Texture: {image: \"nope.jpg\", "
+     "x_offset: 0, y_offset: 0}}, albedo: 1, surface: Diffuse}}\n", host.E_SCHEMA, "Could not load texture file nope.jpg"),
+    ("bodies:\n  - Sphere: {center: [0,0,0], radius: 1, material: {coloration: {Color: \"#ffffff\"}, albedo: 1, "
+     "surface: Reflecting}}\n", host.E_SCHEMA, "Reflecting"),                           # not a unit variant
+    ("a: [1, 2\n", host.E_FORMAT, "unterminated flow"),
+    ("a: &x 1\n", host.E_UNSUPPORTED, "anchors"),
+    ("a: |\n  text\n", host.E_UNSUPPORTED, "block scalars"),
+    ("a: 1\n---\nb: 2\n", host.E_UNSUPPORTED, "multi-document"),
+    ("\tfov: 1\n", host.E_FORMAT, "tab"),
+])
+def test_errors_mirror_serde(text, code, needle):
+    with pytest.raises(host.HostError) as e:
+        host.parse_scene(text)
+    assert e.value.code == code, str(e.value)
+    assert needle in str(e.value), str(e.value)
+    assert str(e.value).startswith("Could not load YAML")  # src/main.rs:118
+
+
+def test_depth_limit_only_lowers():
+    text = "maxRecursionDepth: 6\n"
+    assert host.parse_scene(text, max_depth_limit=4).max_recursion_depth == 4  # --draft, main.rs:119-123
+    assert host.parse_scene(text, max_depth_limit=9).max_recursion_depth == 6
+
+
+# ------------------------------------------------------------------------------------ codecs
+@pytest.mark.parametrize("key,shape", [
+    ("texture/./textures/clay-ground-seamless.jpg", (1500, 1500, 3)),        # progressive, 4:4:4, Adobe
+    ("texture/./textures/land_ocean_ice_cloud_2048.jpg", (1024, 2048, 3)),   # baseline, 4:4:4, Adobe
+    ("texture/textures/tile1/color.jpg", (512, 512, 3)),                     # baseline, 4:2:0 (H2V2)
+])
+def test_jpeg_decoder_agrees_with_libjpeg_within_idct_tolerance(key, shape):
+    """Entropy decoding is exact; IDCT / upsampling / colour conversion legitimately differ between
+    decoders by a few LSB.  (Equality with the REFERENCE's decoder is pinned by test_oracle_golden.)"""
+    from PIL import Image
+
+    mine = host.decode_jpeg(_bundle()[key])
+    assert mine.shape == shape
+    theirs = np.asarray(Image.open(io.BytesIO(_bundle()[key])).convert("RGB"))
+    d = np.abs(mine.astype(np.int32) - theirs.astype(np.int32))
+    assert d.max() <= 4 and d.mean() < 0.1
+
+
+def test_jpeg_variants_roundtrip_through_pillow_encoder():
+    """Grey, 4:2:2 (H2V1), restart intervals, progressive+subsampled, odd sizes."""
+    from PIL import Image
+
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    base = np.asarray(Image.fromarray(base).resize((101, 67), Image.BILINEAR))  # smooth-ish, odd size
+    cases = [dict(subsampling=0), dict(subsampling=1), dict(subsampling=2), dict(subsampling=2, progressive=True),
+             dict(subsampling=0, progressive=True), dict(subsampling=2, restart_marker_blocks=3),
+             dict(subsampling=1, progressive=True, restart_marker_rows=1), dict(grey=True), dict(grey=True, progressive=True)]
+    for kw in cases:
+        grey = kw.pop("grey", False)
+        im = Image.fromarray(base).convert("L") if grey else Image.fromarray(base)
+        buf = io.BytesIO()
+        im.save(buf, "JPEG", quality=90, **kw)
+        mine = host.decode_jpeg(buf.getvalue())
+        theirs = np.asarray(Image.open(io.BytesIO(buf.getvalue())))
+        theirs = theirs[..., None] if theirs.ndim == 2 else theirs
+        assert mine.shape == theirs.shape, kw
+        d = np.abs(mine.astype(np.int32) - theirs.astype(np.int32))
+        # fancy-upsampling edge handling differs by design (stb-style vs libjpeg): a loose bound
+        assert d.mean() < 1.0 and d.max() <= 24, (kw, d.max(), d.mean())
+
+
+def test_jpeg_rejects_garbage():
+    good = _bundle()["texture/textures/tile1/color.jpg"]
+    for bad, code in ((b"", host.E_FORMAT), (b"\x89PNG", host.E_FORMAT), (good[:200], host.E_FORMAT)):
+        with pytest.raises(host.HostError) as e:
+            host.decode_jpeg(bad)
+        assert e.value.code == code
+
+
+def test_png_roundtrip_and_against_pillow(tmp_path):
+    from PIL import Image
+
+    rng = np.random.default_rng(9)
+    for ch in (1, 3, 4):
+        a = rng.integers(0, 256, (33, 47, ch), dtype=np.uint8)
+        a[5:20, 3:30] = 77  # something compressible
+        data = host.encode_png(a)
+        back = host.decode_png(data)
+        want = np.repeat(a, 3, axis=2) if ch == 1 else a
+        assert np.array_equal(back, want)
+        pil = np.asarray(Image.open(io.BytesIO(data)))
+        assert np.array_equal(pil if pil.ndim == 3 else pil[..., None], a)
+    # decode what another encoder wrote: palette, 1-bit grey, interlaced RGBA, grey+alpha
+    img = Image.fromarray(rng.integers(0, 256, (19, 23, 3), dtype=np.uint8))
+    for mode, kw in (("P", {}), ("1", {}), ("RGBA", {}), ("LA", {}), ("L", {}), ("RGB", {"optimize": True})):
+        im = img.convert(mode)
+        buf = io.BytesIO()
+        im.save(buf, "PNG", **kw)
+        mine = host.decode_png(buf.getvalue())
+        want = np.asarray(im.convert("RGBA" if mine.shape[2] == 4 else "RGB"))
+        assert np.array_equal(mine, want), mode
+    p = str(tmp_path / "x.png")
+    host.save_png(p, a)
+    assert np.array_equal(host.open_image(p), a)
+
+
+def test_golden_pngs_decode_like_pillow():
+    from PIL import Image
+
+    for name in ("test1", "test2", "test3"):
+        data = _bundle()[f"golden/{name}.png"]
+        mine = host.decode_png(data)
+        theirs = np.asarray(Image.open(io.BytesIO(data)).convert("RGBA" if mine.shape[2] == 4 else "RGB"))
+        assert np.array_equal(mine, theirs)
+
+
+# ------------------------------------------------------------------------------------ CLI (src/main.rs:143-178)
+def test_cli_resolution_arguments_like_the_reference_tests():
+    P = host.cli_parse
+    assert P(["x", "file"])[:3] == (800, 600, None)
+    assert P(["x", "--width", "640", "--height", "480", "file"])[:2] == (640, 480)
+    assert P(["x", "--hd", "file"])[:2] == (1920, 1080)
+    assert P(["x", "--hd", "--4k", "file"])[:2] == (3840, 2160)
+    assert P(["x", "--hd", "--width", "2000", "file"])[:2] == (2000, 1080)
+    # it_parses_draft_argument
+    assert P(["x", "--hd", "--width", "2000", "--draft", "file"])[:3] == (800, 600, 4)
+    # forms clap accepts
+    assert P(["x", "-w", "320", "-h240", "--output=o.png", "scene.yml"]) == (320, 240, None, False, "scene.yml", "o.png")
+    assert P(["x", "--4k", "--hd", "--preview", "a/b.scene.yml"]) == (1920, 1080, None, True, "a/b.scene.yml", "a/b.scene.png")
+    assert P(["x", "noext"])[5] == "noext.png"
+    assert P(["x", "dir.d/.hidden"])[5] == "dir.d/.hidden.png"
+
+
+@pytest.mark.parametrize("argv,needle", [
+    (["x"], "required arguments"), (["x", "--width", "abc", "f"], "Could not parse width"),
+    (["x", "--height", "-3", "f"], "Could not parse height"), (["x", "--bogus", "f"], "wasn't expected"),
+    (["x", "a", "b"], "wasn't expected"), (["x", "--width"], "requires a value"), (["x", ".."], "Could not guess output filename"),
+])
+def test_cli_usage_errors(argv, needle):
+    with pytest.raises(host.HostError) as e:
+        host.cli_parse(argv)
+    assert e.value.code == host.E_USAGE and needle in str(e.value)
+
+
+def test_cli_binary_fails_loudly_without_a_gpu(tmp_path):
+    """The CLI has no CPU fallback: on a box without an sm_100 device the upload fails, status 101
+    (the reference's panic status); usage errors exit 1 like clap."""
+    if not os.path.exists(host.CLI_PATH):
+        pytest.skip("CLI not built")
+    from raingun_b200 import device_count
+
+    scene = tmp_path / "s.yml"
+    scene.write_text(example_yaml("test2"))
+    r = subprocess.run([host.CLI_PATH], capture_output=True, text=True)
+    assert r.returncode == 1 and "USAGE" in r.stderr
+    if device_count() == 0:
+        r = subprocess.run([host.CLI_PATH, "--draft", str(scene)], capture_output=True, text=True)
+        assert r.returncode == 101 and "Could not upload the scene" in r.stderr
+        assert not (tmp_path / "s.png").exists()
