@@ -160,6 +160,8 @@ def main() -> int:
     ap.add_argument("--schedule", default="steal", choices=["steal", "static"])
     ap.add_argument("--tile-rows", type=int, default=8)
     ap.add_argument("--gather", default="reduce", choices=["reduce", "p2p"])
+    ap.add_argument("--inflight", type=int, default=2,
+                    help="N>1: wavefront batches each rank keeps in flight (scene handle + stream + host thread each)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget (N=1)")
     ap.add_argument("--reference-budget", type=float, default=150.0, help="--impl reference: total seconds")
     ap.add_argument("--no-roofline", action="store_true")
@@ -220,6 +222,23 @@ def main() -> int:
 
     scene = rg.Scene(data, device=local_rank)
     scene.set_accel(accel)
+    inflight = max(1, args.inflight) if world > 1 else 1
+    side_streams = [torch.cuda.Stream(device) for _ in range(inflight - 1)]
+
+    def make_lanes(first_scene):
+        """The rank's in-flight batch lanes: (scene handle, CUDA stream) each; lane 0 is the given scene."""
+        lanes = [(first_scene, sptr)]
+        for s_ in side_streams:
+            extra = rg.Scene(data, device=local_rank)
+            extra.set_accel(accel)
+            lanes.append((extra, s_.cuda_stream))
+        return lanes
+
+    def lane_renderers(lanes):
+        return [(lambda rows, out, sc_=sc_, st_=st_: sc_.render_rowlist_device(w, h, rows, out.data_ptr(), st_))
+                for sc_, st_ in lanes]
+
+    lanes = make_lanes(scene)
     staging = torch.empty((h * w * 4,), dtype=torch.uint8, device=device)
     frame_buf = torch.empty((h, w, 4), dtype=torch.uint8, device=device) if world > 1 else None
     host_frame = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()
@@ -227,14 +246,14 @@ def main() -> int:
 
     gathered = {}
 
-    def step_resident(sc):
+    def step_resident(lanes_):
         """One frame, inputs (scene) and output resident in HBM.  Returns (rays, launches, stats)."""
         if world == 1:
-            st = sc.render_rows_device(w, h, 0, h, staging.data_ptr(), sptr)
+            st = lanes_[0][0].render_rows_device(w, h, 0, h, staging.data_ptr(), sptr)
             return st.rays, st.gpu_launches, st
         frame_counter[0] += 1
         res = render_frame_sharded(
-            lambda rows, out: sc.render_rowlist_device(w, h, rows, out.data_ptr(), sptr), w, h, rank, world,
+            lane_renderers(lanes_), w, h, rank, world,
             frame_counter[0], device, tile_rows=args.tile_rows, schedule=args.schedule, staging=staging,
             gather_mode=args.gather, frame_buf=frame_buf)
         gathered["frame"] = res.frame   # rank 0: the gathered (H, W, 4) frame in HBM
@@ -243,7 +262,7 @@ def main() -> int:
 
     # ---- device-resident arm: `value`
     for _ in range(args.warmup):
-        step_resident(scene)
+        step_resident(lanes)
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -253,7 +272,7 @@ def main() -> int:
     rays = launches = 0
     last_stats = None
     for _ in range(args.steps):
-        r, l, last_stats = step_resident(scene)
+        r, l, last_stats = step_resident(lanes)
         rays += r
         launches += l
     e1.record(stream)
@@ -271,18 +290,22 @@ def main() -> int:
         data.body_kind, data.body_geom, data.coloration_kind, data.color, data.texture_id, data.texture_offset,
         data.albedo, data.surface_kind, data.surface_param, data.light_kind, data.light_vec, data.light_color,
         data.light_intensity)) + sum(t.nbytes for t in data.textures))
-    scene.close()
+    for sc_, _ in lanes:
+        sc_.close()
 
     def step_e2e():
         sc = rg.Scene(data, device=local_rank)
         sc.set_accel(accel)
         if world == 1:
             r = sc.render_rows_into(w, h, 0, h, host_frame.data_ptr()).rays
+            sc.close()
         else:
-            r, _, _ = step_resident(sc)   # row tiles gathered on rank 0's GPU
+            ls = make_lanes(sc)            # every lane re-uploads the scene (counted in h2d_bytes_per_step)
+            r, _, _ = step_resident(ls)    # row tiles gathered on rank 0's GPU
             if rank == 0:
                 host_frame.copy_(gathered["frame"])
-        sc.close()
+            for sc_, _ in ls:
+                sc_.close()
         return r
 
     for _ in range(min(args.warmup, 2)):
@@ -353,10 +376,10 @@ def main() -> int:
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.workload, spec, data, {
                 "accel": accel_used, "pipeline": "wavefront",
-                "parallelism": f"row-tiles x{world} ({args.schedule}, {args.tile_rows}-row tiles, gather={args.gather})" if world > 1 else "1 GPU",
+                "parallelism": f"row-tiles x{world} ({args.schedule}, {args.tile_rows}-row tiles, {inflight} batches in flight per GPU, gather={args.gather})" if world > 1 else "1 GPU",
                 "l2": "per-frame working set (ray queues + nodes, several GB) exceeds the 126 MB L2; no explicit flush"}),
             "rays_per_frame": rays // max(1, args.steps),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": desc_bytes * world,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": desc_bytes * world * inflight,
                     "d2h_bytes_per_step": h * w * 4, "ms_per_step": e2e_s / max(1, args.steps) * 1e3,
                     "what": "rg_scene_create (scene H2D) + render + RGBA8 frame D2H into pinned host memory + rg_scene_destroy, per step"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "brute_force": brute,

@@ -125,7 +125,9 @@ enum {
     RG_OPT_ACCEL = 2,
     RG_OPT_MAX_DEPTH = 3,    /* like main.rs:119-123: lowers max_recursion_depth  */
     RG_OPT_BATCH_PIXELS = 4, /* pixels per wavefront batch (0 = automatic)         */
-    RG_OPT_VERIFY_CULL = 5   /* debug: count FP32-culled pairs the FP64 test hits  */
+    RG_OPT_VERIFY_CULL = 5,  /* debug: count FP32-culled pairs the FP64 test hits  */
+    RG_OPT_OVERLAP = 6       /* shadow side of a level concurrent with the next level's path side:
+                                0 = automatic (on with the grid tracer), 1 = off, 2 = on */
 };
 
 /* Counters and timings of one render call.  A "ray" is one `Scene::trace`

@@ -58,12 +58,18 @@ void DeviceBuffer::release() {
     cap = 0;
 }
 void WavefrontScratch::release() {
-    ray[0].release(); ray[1].release(); hit_t.release(); hit_body.release(); sray.release();
-    s_tmax.release(); s_ab.release(); s_lit.release(); lit_bc.release(); lit_node.release();
+    ray[0].release(); ray[1].release(); hit_t.release(); hit_body.release();
+    for (int p = 0; p < 2; ++p) {
+        sray[p].release(); s_tmax[p].release(); s_ab[p].release(); s_lit[p].release(); lit_bc[p].release(); lit_node[p].release();
+    }
     for (auto &b : nodes) b.release();
     nodes.clear();
     for (auto e : events) cudaEventDestroy(e);
     events.clear();
+    for (auto e : sync_events) cudaEventDestroy(e);
+    sync_events.clear();
+    if (aux) cudaStreamDestroy(aux);
+    aux = nullptr;
 }
 
 // Scratch arenas outlive a scene: destroying a scene parks its (possibly multi-GB) wavefront
@@ -79,7 +85,9 @@ struct ParkedContext {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 static std::mutex g_park_mutex;
-static std::map<int, ParkedContext> g_parked;
+// a few per device: a multi-GPU host keeps several batches (scene handles) in flight per GPU
+static std::map<int, std::vector<ParkedContext>> g_parked;
+constexpr size_t kMaxParkedPerDevice = 4;
 
 void *SceneArena::alloc(size_t bytes) {
     bytes = (bytes + 255) & ~(size_t)255;
@@ -352,9 +360,11 @@ void rg_scene_destroy(rg_scene *sc) {
     for (auto a : sc->tex_arrays) cudaFreeArray(a);
     {
         std::lock_guard<std::mutex> lock(g_park_mutex);
-        ParkedContext &slot = g_parked[sc->device];
-        if (!slot.used && sc->stream) {   // park the device-side context for the next scene on this device
+        std::vector<ParkedContext> &parked = g_parked[sc->device];
+        if (parked.size() < kMaxParkedPerDevice && sc->stream) {   // park the device-side context for the next scene on this device
             if (sc->h_frame) cudaFreeHost(sc->h_frame);
+            parked.emplace_back();
+            ParkedContext &slot = parked.back();
             slot.used = true;
             slot.wf = std::move(sc->wf);
             slot.frame = sc->frame;
@@ -407,8 +417,9 @@ int rg_scene_create(const rg_scene_desc *desc, int32_t device, rg_scene **out) {
     {
         std::lock_guard<std::mutex> lock(g_park_mutex);
         auto it = g_parked.find(device);
-        if (it != g_parked.end() && it->second.used) {   // adopt the context the last scene left behind
-            ParkedContext &slot = it->second;
+        if (it != g_parked.end() && !it->second.empty()) {   // adopt a context an earlier scene left behind
+            ParkedContext slot = std::move(it->second.back());
+            it->second.pop_back();
             sc->wf = std::move(slot.wf);
             sc->frame = slot.frame;
             sc->rowlist = slot.rowlist;
@@ -418,7 +429,6 @@ int rg_scene_create(const rg_scene_desc *desc, int32_t device, rg_scene **out) {
             sc->h_counters = slot.h_counters;
             sc->stream = slot.stream;
             for (int k = 0; k < 4; ++k) sc->ev[k] = slot.ev[k];
-            slot = ParkedContext{};
         }
     }
     if (!sc->stream) {
@@ -455,6 +465,10 @@ int rg_scene_set_option(rg_scene *sc, int32_t key, int64_t value) {
             return RG_OK;
         case RG_OPT_VERIFY_CULL:
             sc->verify_cull = (int)value;
+            return RG_OK;
+        case RG_OPT_OVERLAP:
+            if (value < 0 || value > 2) break;
+            sc->overlap = (int)value;
             return RG_OK;
         default: break;
     }

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
         if (idle == 0xffffffffu && exhausted) break;
         if (!exhausted && (__popc(idle) >= a.g_refill)) {
             uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&a.ctr->fetch, (unsigned)__popc(idle));
+            if (lane == 0) base = atomicAdd(a.fetch, (unsigned)__popc(idle));
             base = __shfl_sync(0xffffffffu, base, 0);
             exhausted = base + (uint32_t)__popc(idle) >= a.n;
             const uint32_t ri = base + __popc(idle & lanemask_lt);

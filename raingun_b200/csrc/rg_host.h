@@ -45,14 +45,18 @@ struct SceneArena {
 struct WavefrontScratch {
     DeviceBuffer ray[2];        // ping-pong path-ray queues: 3 x double2 per ray
     DeviceBuffer hit_t, hit_body;
-    DeviceBuffer sray;          // shadow-ray queue: 3 x double2 per ray
-    DeviceBuffer s_tmax;        // light.distance(hit_point) per shadow ray
-    DeviceBuffer s_ab;          // (max(n.L,0), intensity) per shadow ray
-    DeviceBuffer s_lit;         // in_light byte per shadow ray
-    DeviceBuffer lit_bc;        // float4 (body colour, albedo) per lit hit
-    DeviceBuffer lit_node;      // node index per lit hit
+    // Shadow-side buffers exist twice (level parity): the shadow trace + diffuse of level d run on
+    // the auxiliary stream WHILE the main stream traces and shades level d+1.
+    DeviceBuffer sray[2];       // shadow-ray queue: 3 x double2 per ray
+    DeviceBuffer s_tmax[2];     // light.distance(hit_point) per shadow ray
+    DeviceBuffer s_ab[2];       // (max(n.L,0), intensity) per shadow ray
+    DeviceBuffer s_lit[2];      // in_light byte per shadow ray
+    DeviceBuffer lit_bc[2];     // float4 (body colour, albedo) per lit hit
+    DeviceBuffer lit_node[2];   // node index per lit hit
     std::vector<DeviceBuffer> nodes;   // per level: NodeA float4 + NodeB uint4
     std::vector<cudaEvent_t> events;   // timing events of the trace launches, reused across frames
+    cudaStream_t aux = nullptr;        // shadow-side stream (created on first use)
+    std::vector<cudaEvent_t> sync_events;   // cross-stream dependencies (no timing), reused across frames
     void release();
 };
 
@@ -79,6 +83,7 @@ struct rg_scene {
     uint32_t scene_max_depth = 0;          // as given in the desc
     uint64_t batch_pixels = 0;
     int verify_cull = 0;
+    int overlap = 0;                       // RG_OPT_OVERLAP: 0 auto (on with the grid tracer), 1 off, 2 on
     // derived
     uint32_t n_bodies = 0;
     int sm_count = 0;

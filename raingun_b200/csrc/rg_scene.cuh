@@ -90,7 +90,7 @@ struct DCounters {
     unsigned int q_next;               // wavefront: children emitted into the next level
     unsigned int q_lit;                // wavefront: hits that need shadow rays
     unsigned int fetch;                // persistent trace kernels: next unclaimed ray of the queue
-    unsigned int pad;
+    unsigned int fetch_shadow;         // ... of the shadow queue (the two kinds of trace run concurrently)
 };
 
 }  // namespace rg

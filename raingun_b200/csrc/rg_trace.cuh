@@ -41,6 +41,7 @@ struct TraceArgs {
     uint32_t *out_body;      // nearest: original body index or kNoBody
     uint8_t *out_lit;        // ANY: 1 = in light
     DCounters *ctr;
+    unsigned int *fetch;     // persistent kernels: the ray counter of THIS launch (ctr->fetch / ctr->fetch_shadow)
     int verify;              // RG_OPT_VERIFY_CULL
     int g_refill, g_quorum, g_burst;   // persistent grid kernel tuning (rg_grid.cuh)
 };

@@ -253,11 +253,12 @@ static RayQueue make_queue(DeviceBuffer &b, size_t cap) {
 struct EventPool {
     std::vector<cudaEvent_t> &ev;   // owned by the scratch (kept across frames)
     size_t used = 0;
-    explicit EventPool(std::vector<cudaEvent_t> &store) : ev(store) {}
+    unsigned flags;
+    explicit EventPool(std::vector<cudaEvent_t> &store, unsigned f = cudaEventDefault) : ev(store), flags(f) {}
     cudaEvent_t get() {
         if (used == ev.size()) {
             cudaEvent_t e;
-            if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&e, flags) != cudaSuccess) return nullptr;
             ev.push_back(e);
         }
         return ev[used++];
@@ -277,7 +278,8 @@ static int launch_trace(rg_scene *sc, const TraceArgs &ta, bool use_grid, cudaSt
         const unsigned blocks = std::min<unsigned>(want, (unsigned)(sc->sm_count * bps));
         TraceArgs tuned = ta;
         tuned.g_refill = t_refill; tuned.g_quorum = t_quorum; tuned.g_burst = t_burst;
-        RG_CUDA(cudaMemsetAsync(&ta.ctr->fetch, 0, sizeof(unsigned int), stream));
+        tuned.fetch = ANY ? &ta.ctr->fetch_shadow : &ta.ctr->fetch;   // the two kinds may run concurrently
+        RG_CUDA(cudaMemsetAsync(tuned.fetch, 0, sizeof(unsigned int), stream));
         k_trace_grid<ANY><<<blocks, kGridTraceThreads, 0, stream>>>(sc->ds, tuned);
     } else {
         // register tiling R: 4 rays per thread when there is enough work to fill the chip
@@ -310,7 +312,7 @@ static int launch_trace(rg_scene *sc, const TraceArgs &ta, bool use_grid, cudaSt
 
 static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0, uint32_t y1,
                         const uint32_t *d_rows, uchar4 *d_out, cudaStream_t stream, rg_stats *st, bool use_grid, EventPool &events,
-                        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> &trace_spans) {
+                        EventPool &sync_events, std::vector<std::pair<cudaEvent_t, cudaEvent_t>> &trace_spans) {
     const uint64_t npix64 = (uint64_t)(y1 - y0) * width;
     if (npix64 == 0) return RG_OK;
     if (npix64 > 0x7FFFFFFFull) { set_error("batch of %llu pixels is too large", (unsigned long long)npix64); return RG_E_NOMEM; }
@@ -321,6 +323,21 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
     DCounters *dc = sc->d_counters, *hc = sc->h_counters;
     int rc;
     auto blocks = [](uint64_t n) { return (unsigned)((n + 255) / 256); };
+
+    // Two-stream schedule.  The shadow side of level d (any-hit trace + k_diffuse) depends only on
+    // k_shade(d); the path side of level d+1 (nearest trace + k_shade) depends only on k_shade(d)
+    // too.  With the grid tracer both are latency-bound persistent kernels with long tails, so the
+    // shadow side runs on an auxiliary stream, concurrently with the next level's path side; its
+    // buffers exist twice (level parity) and k_shade(d+2) waits for the shadow side of level d.
+    // The brute-force tracer fills the chip on its own and keeps the single-stream order (its
+    // per-kernel times are also what the roofline figure is computed from).
+    const bool overlap = L > 0 && (sc->overlap == 2 || (sc->overlap == 0 && use_grid));
+    cudaStream_t aux = stream;
+    if (overlap) {
+        if (!wf.aux) RG_CUDA(cudaStreamCreateWithFlags(&wf.aux, cudaStreamNonBlocking));
+        aux = wf.aux;
+    }
+    cudaEvent_t shadow_done[2] = {nullptr, nullptr};   // last shadow-side work that used the parity's buffers
 
     std::vector<uint32_t> level_n;
     uint32_t n = npix, d = 0;
@@ -345,12 +362,13 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
         if ((rc = wf.hit_body.reserve((size_t)n * 4))) return rc;
         DeviceBuffer &nextbuf = wf.ray[(d + 1) & 1];
         if ((rc = nextbuf.reserve((size_t)std::max<uint64_t>(next_cap, 1) * 48))) return rc;
-        if ((rc = wf.sray.reserve((size_t)std::max<uint64_t>(shadow_cap, 1) * 48))) return rc;
-        if ((rc = wf.s_tmax.reserve((size_t)std::max<uint64_t>(shadow_cap, 1) * 8))) return rc;
-        if ((rc = wf.s_ab.reserve((size_t)std::max<uint64_t>(shadow_cap, 1) * 8))) return rc;
-        if ((rc = wf.s_lit.reserve((size_t)std::max<uint64_t>(shadow_cap, 1)))) return rc;
-        if ((rc = wf.lit_bc.reserve((size_t)n * 16))) return rc;
-        if ((rc = wf.lit_node.reserve((size_t)n * 4))) return rc;
+        const int p = overlap ? (int)(d & 1u) : 0;   // parity of the shadow-side buffers
+        if ((rc = wf.sray[p].reserve((size_t)std::max<uint64_t>(shadow_cap, 1) * 48))) return rc;
+        if ((rc = wf.s_tmax[p].reserve((size_t)std::max<uint64_t>(shadow_cap, 1) * 8))) return rc;
+        if ((rc = wf.s_ab[p].reserve((size_t)std::max<uint64_t>(shadow_cap, 1) * 8))) return rc;
+        if ((rc = wf.s_lit[p].reserve((size_t)std::max<uint64_t>(shadow_cap, 1)))) return rc;
+        if ((rc = wf.lit_bc[p].reserve((size_t)n * 16))) return rc;
+        if ((rc = wf.lit_node[p].reserve((size_t)n * 4))) return rc;
 
         // nearest hits of this level
         TraceArgs ta{};
@@ -371,15 +389,15 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
         LevelBuffers lb{};
         lb.cur = cur;
         lb.next = make_queue(nextbuf, (size_t)std::max<uint64_t>(next_cap, 1));
-        lb.shadow = make_queue(wf.sray, (size_t)std::max<uint64_t>(shadow_cap, 1));
+        lb.shadow = make_queue(wf.sray[p], (size_t)std::max<uint64_t>(shadow_cap, 1));
         lb.hit_t = wf.hit_t.as<double>();
         lb.hit_body = wf.hit_body.as<uint32_t>();
         lb.node_a = wf.nodes[d].as<float4>();
         lb.node_b = reinterpret_cast<uint4 *>(wf.nodes[d].as<float4>() + n);
-        lb.s_tmax = wf.s_tmax.as<double>();
-        lb.s_ab = wf.s_ab.as<float2>();
-        lb.lit_bc = wf.lit_bc.as<float4>();
-        lb.lit_node = wf.lit_node.as<uint32_t>();
+        lb.s_tmax = wf.s_tmax[p].as<double>();
+        lb.s_ab = wf.s_ab[p].as<float2>();
+        lb.lit_bc = wf.lit_bc[p].as<float4>();
+        lb.lit_node = wf.lit_node[p].as<uint32_t>();
         lb.n = n;
         // shadow-queue order: hit-major (the L rays of a hit adjacent; default) or light-major
         static const bool light_major = [] { const char *e = getenv("RG_SHADOW_LIGHT_MAJOR"); return e && atoi(e) != 0; }();
@@ -387,6 +405,7 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
         lb.shadow_sj = light_major ? 1u : L;
         lb.can_spawn = can_spawn ? 1u : 0u;
         RG_CUDA(cudaMemsetAsync(&dc->q_next, 0, 2 * sizeof(unsigned int), stream));
+        if (shadow_done[p]) RG_CUDA(cudaStreamWaitEvent(stream, shadow_done[p], 0));   // level d-2 still reads these buffers
         k_shade<<<blocks(n), 256, 0, stream>>>(ds, lb, dc);
         RG_CUDA(cudaGetLastError());
         st->gpu_launches++;
@@ -394,6 +413,8 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
         RG_CUDA(cudaStreamSynchronize(stream));
         const uint32_t n_next = hc->q_next, n_lit = hc->q_lit;
 
+        // shadow side: on `aux` (== stream without overlap).  The host has just synchronised the
+        // main stream, so everything k_shade(d) wrote is visible to work submitted to aux now.
         if (n_lit && L) {
             TraceArgs sa{};
             sa.q = lb.shadow;
@@ -401,30 +422,37 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
             sa.n = n_lit * L;
             sa.seg_len = light_major ? n_lit : 0u;
             sa.seg_stride = n;
-            sa.out_lit = wf.s_lit.as<uint8_t>();
+            sa.out_lit = wf.s_lit[p].as<uint8_t>();
             sa.ctr = dc;
             sa.verify = sc->verify_cull == 1;
             cudaEvent_t s0 = events.get(), s1 = events.get();
-            RG_CUDA(cudaEventRecord(s0, stream));
-            if ((rc = launch_trace<true>(sc, sa, use_grid, stream))) return rc;
-            RG_CUDA(cudaEventRecord(s1, stream));
+            RG_CUDA(cudaEventRecord(s0, aux));
+            if ((rc = launch_trace<true>(sc, sa, use_grid, aux))) return rc;
+            RG_CUDA(cudaEventRecord(s1, aux));
             trace_spans.emplace_back(s0, s1);
-            if (sc->verify_cull >= 2) k_verify_trace<true><<<(sa.n + 127) / 128, 128, 0, stream>>>(ds, sa, (int)d);
+            if (sc->verify_cull >= 2) k_verify_trace<true><<<(sa.n + 127) / 128, 128, 0, aux>>>(ds, sa, (int)d);
             st->gpu_launches++;
             st->rays_shadow += (uint64_t)n_lit * L;
         }
         if (n_lit) {
-            k_diffuse<<<blocks(n_lit), 256, 0, stream>>>(ds, lb.lit_bc, lb.lit_node, lb.s_ab, wf.s_lit.as<uint8_t>(),
-                                                         lb.node_a, n_lit, lb.shadow_sl, lb.shadow_sj);
+            k_diffuse<<<blocks(n_lit), 256, 0, aux>>>(ds, lb.lit_bc, lb.lit_node, lb.s_ab, wf.s_lit[p].as<uint8_t>(),
+                                                      lb.node_a, n_lit, lb.shadow_sl, lb.shadow_sj);
             RG_CUDA(cudaGetLastError());
             st->gpu_launches++;
+            if (overlap) {
+                shadow_done[p] = sync_events.get();
+                RG_CUDA(cudaEventRecord(shadow_done[p], aux));
+            }
         }
         level_n.push_back(n);
         cur = lb.next;
         n = n_next;
         ++d;
     }
-    // bottom-up colour combination, then quantise level 0
+    // bottom-up colour combination (after the shadow side has delivered every diffuse term), then
+    // quantise level 0
+    for (int q = 0; q < 2; ++q)
+        if (shadow_done[q]) RG_CUDA(cudaStreamWaitEvent(stream, shadow_done[q], 0));
     for (int lvl = (int)level_n.size() - 1; lvl >= 0; --lvl) {
         const uint32_t ln = level_n[lvl];
         float4 *a = wf.nodes[lvl].as<float4>();
@@ -451,6 +479,7 @@ int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0,
     st->accel_used = use_grid ? RG_ACCEL_GRID : RG_ACCEL_BRUTE;
 
     EventPool events(sc->wf.events);
+    EventPool sync_events(sc->wf.sync_events, cudaEventDisableTiming);
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_spans;
     const uint32_t rows = y1 - y0;
     const uint64_t batch_pixels = sc->batch_pixels ? sc->batch_pixels : (16ull << 20);
@@ -459,6 +488,7 @@ int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0,
     for (;;) {   // a ray tree larger than device memory restarts the render with half the rows per batch
         *st = st0;
         events.used = 0;
+        sync_events.used = 0;
         trace_spans.clear();
         RG_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(DCounters), stream));
         RG_CUDA(cudaEventRecord(sc->ev[0], stream));
@@ -466,11 +496,12 @@ int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0,
         for (uint32_t y = y0; y < y1 && rc == RG_OK;) {
             const uint32_t ye = (uint32_t)std::min<uint64_t>((uint64_t)y + batch_rows, y1);
             rc = render_batch(sc, width, height, y, ye, d_rows, d_out + (size_t)(y - y0) * width, stream, st, use_grid,
-                              events, trace_spans);
+                              events, sync_events, trace_spans);
             y = ye;
         }
         if (rc == RG_E_NOMEM && batch_rows > 1) {
             cudaStreamSynchronize(stream);
+            if (sc->wf.aux) cudaStreamSynchronize(sc->wf.aux);
             sc->wf.release();
             batch_rows = (batch_rows + 1) / 2;
             continue;

@@ -9,14 +9,22 @@ in guided chunks (large first, small last).  The only exchange is the final gath
 RGBA8 tiles into rank 0's frame: point-to-point sends over NVLink (NCCL send/recv), i.e.
 rayon's ``collect`` (rendering.rs:34-35).
 
+A batch of few rows cannot fill a B200 (its 8 bounce levels are ~40 short, latency-bound launches
+with a host read-back each), so a rank may keep SEVERAL batches in flight: ``render_rowlist`` can
+be a list of renderers (one scene handle + CUDA stream each), driven by one host thread each.  The
+static share is split between them and the stealable tail is claimed by whichever thread runs dry,
+so the fixed cost of a small batch hides under the other thread's kernels.
+
 One process per GPU (torchrun); works unchanged on the gloo backend with CPU tensors, which
 is how the host logic is tested without GPUs (tests/test_dist_gloo.py).
 """
 from __future__ import annotations
 
 import pickle
+import threading
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
-from typing import Callable, List, Optional, Sequence
+from typing import Callable, List, Optional, Sequence, Union
 
 import numpy as np
 import torch
@@ -55,6 +63,21 @@ def guided_chunks(num_tiles: int, world: int, min_chunk: int = 1) -> List[List[i
 def static_chunk(num_tiles: int, world: int, rank: int) -> List[int]:
     """Interleaved static ownership: tile t belongs to rank t % world."""
     return list(range(rank, num_tiles, world))
+
+
+_POOLS = {}
+
+
+def _pool(workers: int) -> ThreadPoolExecutor:
+    if workers not in _POOLS:
+        _POOLS[workers] = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="raingun-batch")
+    return _POOLS[workers]
+
+
+def split_share(tiles: Sequence[int], workers: int) -> List[List[int]]:
+    """A rank's static share dealt round-robin to its in-flight batches (each stays interleaved
+    over the image, so the halves cost about the same)."""
+    return [list(tiles[k::workers]) for k in range(workers)]
 
 
 def hybrid_plan(num_tiles: int, world: int, tail_every: int = 16, min_chunk: int = 2):
@@ -97,7 +120,8 @@ def default_store():
     return dist.distributed_c10d._get_default_store()
 
 
-def render_frame_sharded(render_rowlist: Callable[[np.ndarray, torch.Tensor], object], width: int, height: int,
+def render_frame_sharded(render_rowlist: Union[Callable[[np.ndarray, torch.Tensor], object], Sequence[Callable]],
+                         width: int, height: int,
                          rank: int, world: int, frame_id: int, device: torch.device, store=None,
                          tile_rows: int = DEFAULT_TILE_ROWS, schedule: str = "steal",
                          gather: bool = True, staging: Optional[torch.Tensor] = None,
@@ -105,8 +129,10 @@ def render_frame_sharded(render_rowlist: Callable[[np.ndarray, torch.Tensor], ob
     """Renders one frame across ``world`` ranks.
 
     ``render_rowlist(rows, out)`` must fill ``out`` (a uint8 tensor of ``len(rows)*width*4``
-    bytes on ``device``) with the listed image rows, compacted in list order — on a GPU that is
-    ``Scene.render_rowlist_device``.  ``schedule`` is ``"steal"`` (static interleaved share first, then the
+    bytes on ``device``) with the listed image rows, compacted in list order, and return once they
+    are there — on a GPU that is ``Scene.render_rowlist_device``.  A LIST of such callables keeps
+    that many batches in flight on this rank (one host thread each; see the module docstring).
+    ``schedule`` is ``"steal"`` (static interleaved share first, then the
     work-stealing counter for the tail — see ``hybrid_plan``) or ``"static"`` (interleaved
     ownership only, one batch per rank).
 
@@ -118,42 +144,56 @@ def render_frame_sharded(render_rowlist: Callable[[np.ndarray, torch.Tensor], ob
     nt = n_tiles(height, tile_rows)
     res = ShardResult(frame=None)
     row_bytes = width * 4
+    renderers = list(render_rowlist) if isinstance(render_rowlist, (list, tuple)) else [render_rowlist]
+    workers = len(renderers)
     if staging is None:
         staging = torch.empty((height * row_bytes,), dtype=torch.uint8, device=device)
+    # first[k]: the batch worker k starts with (no counter traffic); claim(): the stealable rest
     if world == 1:
-        pending = iter([list(range(nt))])
-        claim = lambda: next(pending, None)
+        first = split_share(list(range(nt)), workers)
+        claim = lambda: None
     elif schedule == "steal":
         if store is None:
             store = default_store()
-        per_rank, tail_chunks = hybrid_plan(nt, world)
+        per_rank, tail_chunks = hybrid_plan(nt, world, min_chunk=2 if workers == 1 else 1)
         counter = TileCounter(store, f"raingun/tiles/{frame_id}", tail_chunks)
-        own = iter([per_rank[rank]] if per_rank[rank] else [])
-
-        def claim():
-            mine = next(own, None)
-            return mine if mine is not None else counter.claim()
+        first = split_share(per_rank[rank], workers)
+        claim = counter.claim
     elif schedule == "static":
-        pending = iter([static_chunk(nt, world, rank)])
-        claim = lambda: next(pending, None)
+        first = split_share(static_chunk(nt, world, rank), workers)
+        claim = lambda: None
     else:
         raise ValueError(f"unknown schedule {schedule!r}")
 
-    filled_rows = 0
+    lock, claim_lock = threading.Lock(), threading.Lock()
+    state = {"filled": 0}
     my_rows: List[np.ndarray] = []
-    while True:
-        tiles = claim()
-        if tiles is None:
-            break
-        if not tiles:
-            continue
-        res.claims += 1
-        rows = rows_of_tiles(tiles, tile_rows, height)
-        out = staging[filled_rows * row_bytes:(filled_rows + int(rows.size)) * row_bytes]
-        res.stats.append(render_rowlist(rows, out))
-        res.my_tiles.extend(tiles)
-        my_rows.append(rows)
-        filled_rows += int(rows.size)
+
+    def run_worker(k: int) -> None:
+        tiles = first[k]
+        while tiles is not None:
+            if tiles:
+                rows = rows_of_tiles(tiles, tile_rows, height)
+                with lock:   # reserve the output rows of this batch
+                    at = state["filled"]
+                    state["filled"] = at + int(rows.size)
+                out = staging[at * row_bytes:(at + int(rows.size)) * row_bytes]
+                stat = renderers[k](rows, out)
+                with lock:
+                    res.claims += 1
+                    res.stats.append(stat)
+                    res.my_tiles.extend(tiles)
+                    my_rows.append((at, rows))
+            with claim_lock:   # one store round trip at a time per rank
+                tiles = claim()
+
+    if workers == 1:
+        run_worker(0)
+    else:
+        for f in [_pool(workers).submit(run_worker, k) for k in range(workers)]:
+            f.result()
+    filled_rows = state["filled"]
+    my_rows = [r for _, r in sorted(my_rows, key=lambda ar: ar[0])]   # staging order
     rows_all = np.concatenate(my_rows) if my_rows else np.zeros(0, np.uint32)
     if not gather:
         return res

@@ -21,7 +21,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, schedule, out_dir, gather_mode="p2p"):
+def _worker(rank, world, port, schedule, out_dir, gather_mode="p2p", workers=1):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import oracle
@@ -40,7 +40,8 @@ def _worker(rank, world, port, schedule, out_dir, gather_mode="p2p"):
 
     tiles = []
     for frame_id in (1, 2):   # two frames: the counter keys must not collide
-        res = render_frame_sharded(render_rowlist, W, H, rank, world, frame_id, torch.device("cpu"),
+        res = render_frame_sharded(render_rowlist if workers == 1 else [render_rowlist] * workers, W, H, rank, world,
+                                   frame_id, torch.device("cpu"),
                                    tile_rows=TILE, schedule=schedule, gather_mode=gather_mode)
         tiles.append(sorted(res.my_tiles))
         if rank == 0:
@@ -50,10 +51,12 @@ def _worker(rank, world, port, schedule, out_dir, gather_mode="p2p"):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("schedule,gather_mode", [("steal", "p2p"), ("static", "p2p"), ("steal", "reduce")])
-def test_two_ranks_reassemble_the_frame(tmp_path, oracle, schedule, gather_mode):
+@pytest.mark.parametrize("schedule,gather_mode,workers", [("steal", "p2p", 1), ("static", "p2p", 1), ("steal", "reduce", 1),
+                                                          ("steal", "reduce", 2), ("static", "p2p", 3)])
+def test_two_ranks_reassemble_the_frame(tmp_path, oracle, schedule, gather_mode, workers):
+    """workers > 1: several batches in flight per rank (one host thread each) claim from the same counter."""
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), schedule, str(tmp_path), gather_mode), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), schedule, str(tmp_path), gather_mode, workers), nprocs=world, join=True)
     from raingun_b200.synth import make_scene
 
     data, _ = make_scene("C4", spheres=40, depth=4)
@@ -63,7 +66,7 @@ def test_two_ranks_reassemble_the_frame(tmp_path, oracle, schedule, gather_mode)
     t0, t1 = np.load(tmp_path / "tiles0.npy"), np.load(tmp_path / "tiles1.npy")
     assert sorted(t0.tolist() + t1.tolist()) == list(range(n_tiles(H, TILE)))   # every tile exactly once
     if schedule == "static":
-        assert t0.tolist() == static_chunk(n_tiles(H, TILE), 2, 0)
+        assert sorted(t0.tolist()) == static_chunk(n_tiles(H, TILE), 2, 0)
 
 
 def test_schedules_cover_every_tile_once():
