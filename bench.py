@@ -157,10 +157,11 @@ def main() -> int:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C4", choices=["C3", "C4", "C5"])
     ap.add_argument("--accel", default="auto", choices=["auto", "grid", "brute"])
-    ap.add_argument("--schedule", default="steal", choices=["steal", "static"])
+    ap.add_argument("--schedule", default="auto", choices=["auto", "steal", "static"])
     ap.add_argument("--tile-rows", type=int, default=8)
     ap.add_argument("--gather", default="reduce", choices=["reduce", "p2p"])
-    ap.add_argument("--inflight", type=int, default=2,
+    ap.add_argument("--lead", type=float, default=0.6, help="share of a rank's static tiles given to its first in-flight batch")
+    ap.add_argument("--inflight", type=int, default=1,
                     help="N>1: wavefront batches each rank keeps in flight (scene handle + stream + host thread each)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget (N=1)")
     ap.add_argument("--reference-budget", type=float, default=150.0, help="--impl reference: total seconds")
@@ -255,8 +256,9 @@ def main() -> int:
         res = render_frame_sharded(
             lane_renderers(lanes_), w, h, rank, world,
             frame_counter[0], device, tile_rows=args.tile_rows, schedule=args.schedule, staging=staging,
-            gather_mode=args.gather, frame_buf=frame_buf)
+            gather_mode=args.gather, frame_buf=frame_buf, lead=args.lead)
         gathered["frame"] = res.frame   # rank 0: the gathered (H, W, 4) frame in HBM
+        gathered["schedule"] = res.schedule
         return (sum(s.rays for s in res.stats), sum(s.gpu_launches for s in res.stats),
                 res.stats[-1] if res.stats else None)
 
@@ -376,7 +378,7 @@ def main() -> int:
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.workload, spec, data, {
                 "accel": accel_used, "pipeline": "wavefront",
-                "parallelism": f"row-tiles x{world} ({args.schedule}, {args.tile_rows}-row tiles, {inflight} batches in flight per GPU, gather={args.gather})" if world > 1 else "1 GPU",
+                "parallelism": f"row-tiles x{world} ({args.schedule}->{gathered.get('schedule', '?')}, {args.tile_rows}-row tiles, {inflight} batches in flight per GPU, gather={args.gather})" if world > 1 else "1 GPU",
                 "l2": "per-frame working set (ray queues + nodes, several GB) exceeds the 126 MB L2; no explicit flush"}),
             "rays_per_frame": rays // max(1, args.steps),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": desc_bytes * world * inflight,

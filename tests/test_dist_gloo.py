@@ -79,5 +79,8 @@ def test_schedules_cover_every_tile_once():
             per_rank, tail = hybrid_plan(nt, world)
             covered = sorted([t for r in per_rank for t in r] + [t for c in tail for t in c])
             assert covered == list(range(nt)) and len(per_rank) == max(world, 1)
+    from raingun_b200.dist import resolve_schedule
+    assert resolve_schedule("auto", 270, 8) == "static" and resolve_schedule("auto", 270, 32) == "steal"
+    assert resolve_schedule("steal", 270, 8) == "steal"
     assert rows_of_tiles([0, 13], 4, 54).tolist() == [0, 1, 2, 3, 52, 53]             # ragged last tile
     assert rows_of_tiles([], 4, 54).size == 0
