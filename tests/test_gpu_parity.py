@@ -194,3 +194,65 @@ def test_cli_binary_reproduces_the_reference_pngs(tmp_path):
     with rg.Scene(example_scene("test1").with_max_depth_limit(4)) as sc:
         want = sc.render_image(320, 240)
     assert np.array_equal(host.open_image(str(tmp_path / "d.png")), want)
+
+
+# ------------------------------------------------------------------ BASELINE.json's full sizes
+def _full_frame(name):
+    data, spec = make_scene(name, texture_loader=bundled_texture_loader)
+    with rg.Scene(data) as sc:
+        img = sc.render_image(spec.width, spec.height)
+        st = sc.last_stats
+    return data, spec, img, st
+
+
+@pytest.mark.parametrize("name,bands,rays", [
+    ("C3", ((0, 2), (1079, 1083), (2158, 2160)), 26532915),
+    ("C4", ((300, 301), (1079, 1082), (2000, 2001)), 111009057),
+])
+def test_full_size_frames_match_oracle_on_row_bands(oracle, name, bands, rays):
+    """configs[2..3] at their full 3840x2160: the oracle cannot render the whole frame in test time
+    (~5 min on 16 cores for C4) but pixels are independent (rendering.rs:27-35), so full-resolution
+    row bands are an exact check of the full-size frame.  The ray total pins the whole frame."""
+    data, spec, img, st = _full_frame(name)
+    assert st.rays == rays
+    assert (st.err_nan_distance, st.err_transmission_none, st.err_aabb_normal) == (0, 0, 0)
+    assert (img[..., 3] == 255).all()
+    for y0, y1 in bands:
+        ref, _, _ = oracle.render_rows(data, spec.width, spec.height, y0, y1)
+        assert np.array_equal(img[y0:y1], ref), f"{name} rows [{y0},{y1})"
+
+
+def test_full_size_c4_every_strategy_renders_the_same_frame():
+    """Size-independent property at the headline configuration: exact culling (grid), the reference's
+    all-pairs scan (brute force), the one- and two-stream schedules and a row-list split all produce
+    the same 8.3 M pixels and the same ray counts."""
+    data, spec = make_scene("C4")
+    w, h = spec.width, spec.height
+    frames, counts = {}, {}
+    for label, accel, overlap in (("grid", rg.ACCEL_GRID, 0), ("grid-1stream", rg.ACCEL_GRID, 1),
+                                  ("brute", rg.ACCEL_BRUTE, 0), ("brute-2stream", rg.ACCEL_BRUTE, 2)):
+        with rg.Scene(data) as sc:
+            sc.set_accel(accel)
+            sc.set_option(rg._native.OPT_OVERLAP, overlap)
+            frames[label] = sc.render_image(w, h)
+            s = sc.last_stats
+            counts[label] = (s.rays_primary, s.rays_shadow, s.rays_reflection, s.rays_transmission)
+    for label in frames:
+        assert np.array_equal(frames[label], frames["grid"]), label
+        assert counts[label] == counts["grid"], label
+    import torch
+    rows = np.concatenate([np.arange(y, min(h, y + 8), dtype=np.uint32) for y in range(8, h, 24)])   # every third 8-row tile
+    out = torch.empty(rows.size * w * 4, dtype=torch.uint8, device="cuda")
+    with rg.Scene(data) as sc:
+        sc.render_rowlist_device(w, h, rows, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert np.array_equal(out.cpu().numpy().reshape(rows.size, w, 4), frames["grid"][rows])
+
+
+def test_full_size_c5_row_matches_oracle(oracle):
+    """configs[4]: 7680x4320, 100,000 spheres, 4 spherical lights, textured, depth 8 (two wavefront
+    batches).  One full-resolution row through the oracle (~1.7e10 body tests) pins it."""
+    data, spec, img, st = _full_frame("C5")
+    assert st.rays == 673163668 and st.batches == 2
+    y = 2600
+    ref, _, _ = oracle.render_rows(data, spec.width, spec.height, y, y + 1)
+    assert np.array_equal(img[y:y + 1], ref)
