@@ -295,9 +295,13 @@ def main() -> int:
     for sc_, _ in lanes:
         sc_.close()
 
+    upload_s = [0.0]
+
     def step_e2e():
+        t_up = time.perf_counter()
         sc = rg.Scene(data, device=local_rank)
         sc.set_accel(accel)
+        upload_s[0] += time.perf_counter() - t_up   # reported separately as well
         if world == 1:
             r = sc.render_rows_into(w, h, 0, h, host_frame.data_ptr()).rays
             sc.close()
@@ -312,6 +316,7 @@ def main() -> int:
 
     for _ in range(min(args.warmup, 2)):
         step_e2e()
+    upload_s[0] = 0.0
     barrier()
     t0 = time.perf_counter()
     e2e_rays = 0
@@ -337,12 +342,14 @@ def main() -> int:
             sc.render_rows_device(w, h, 0, h, staging.data_ptr(), sptr)
             torch.cuda.synchronize(device)
             tr_ms = dev_ms = 0.0
-            brays = blaunch = 0
+            brays = blaunch = bexact = btests = 0
             for _ in range(bsteps):
                 st = sc.render_rows_device(w, h, 0, h, staging.data_ptr(), sptr)
                 tr_ms += st.ms_trace
                 dev_ms += st.ms_device
                 brays += st.rays
+                bexact += st.exact_tests
+                btests += st.body_tests
                 blaunch += 2 * (st.max_level + 1)
             sc.close()
             fl = flops_per_ray(data)
@@ -355,6 +362,7 @@ def main() -> int:
                         "peak_source": "rg_measure_peaks: register-resident FFMA loop on this GPU, this run (MEASURED_PEAKS.json "
                                        "has no FP32 figure; nominal 74.4 TFLOP/s at 1965 MHz)",
                         "fp64_peak_tflops": fp64_peak,
+                        "fp64_fallthrough_frac": bexact / btests if btests else None,   # pairs the FP32 cull could not reject
                         "share_of_step": tr_ms / dev_ms if dev_ms > 0 else None}
             brute = {"value": brays / (dev_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": dev_ms / bsteps,
                      "ms_trace_kernels": tr_ms / bsteps, "steps": bsteps}
@@ -383,6 +391,7 @@ def main() -> int:
             "rays_per_frame": rays // max(1, args.steps),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": desc_bytes * world * inflight,
                     "d2h_bytes_per_step": h * w * 4, "ms_per_step": e2e_s / max(1, args.steps) * 1e3,
+                    "scene_upload_ms_per_step": upload_s[0] / max(1, args.steps) * 1e3,
                     "what": "rg_scene_create (scene H2D) + render + RGBA8 frame D2H into pinned host memory + rg_scene_destroy, per step"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "brute_force": brute,
             "cpu_baseline": cpu_baseline, "frame_checksum": checksum,
