@@ -159,7 +159,8 @@ def main() -> int:
     ap.add_argument("--accel", default="auto", choices=["auto", "grid", "brute"])
     ap.add_argument("--schedule", default="auto", choices=["auto", "steal", "static"])
     ap.add_argument("--tile-rows", type=int, default=8)
-    ap.add_argument("--gather", default="reduce", choices=["reduce", "p2p"])
+    ap.add_argument("--gather", default="peer", choices=["peer", "reduce", "p2p"],
+                    help="N>1: peer = rows stored straight into rank 0's frame over NVLink by the last kernel (CUDA IPC)")
     ap.add_argument("--lead", type=float, default=0.6, help="share of a rank's static tiles given to its first in-flight batch")
     ap.add_argument("--inflight", type=int, default=1,
                     help="N>1: wavefront batches each rank keeps in flight (scene handle + stream + host thread each)")
@@ -235,7 +236,15 @@ def main() -> int:
             lanes.append((extra, s_.cuda_stream))
         return lanes
 
+    peer_frames = None
+    if world > 1 and args.gather == "peer":
+        from raingun_b200.dist import PeerFrames
+        peer_frames = PeerFrames(w, h, rank, world, local_rank)
+
     def lane_renderers(lanes):
+        if peer_frames is not None:
+            return [(lambda rows, fptr, sc_=sc_, st_=st_: sc_.render_rowlist_scatter(w, h, rows, fptr, st_))
+                    for sc_, st_ in lanes]
         return [(lambda rows, out, sc_=sc_, st_=st_: sc_.render_rowlist_device(w, h, rows, out.data_ptr(), st_))
                 for sc_, st_ in lanes]
 
@@ -256,7 +265,7 @@ def main() -> int:
         res = render_frame_sharded(
             lane_renderers(lanes_), w, h, rank, world,
             frame_counter[0], device, tile_rows=args.tile_rows, schedule=args.schedule, staging=staging,
-            gather_mode=args.gather, frame_buf=frame_buf, lead=args.lead)
+            gather_mode=args.gather, frame_buf=frame_buf, lead=args.lead, peer_frames=peer_frames)
         gathered["frame"] = res.frame   # rank 0: the gathered (H, W, 4) frame in HBM
         gathered["schedule"] = res.schedule
         return (sum(s.rays for s in res.stats), sum(s.gpu_launches for s in res.stats),
@@ -397,6 +406,8 @@ def main() -> int:
             "cpu_baseline": cpu_baseline, "frame_checksum": checksum,
         }
         print(json.dumps(line), flush=True)
+    if peer_frames is not None:
+        peer_frames.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

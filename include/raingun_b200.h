@@ -197,6 +197,23 @@ int rg_render_rowlist_device(rg_scene *scene, uint32_t width, uint32_t height,
                              const uint32_t *rows, uint32_t n_rows, void *d_rgba_out,
                              void *cuda_stream, rg_stats *stats);
 
+/* The same with the gather FUSED into the last kernel: row `rows[k]` is stored at its own place,
+ * `d_frame + rows[k]*width*4`, of a full width*height*4 frame.  `d_frame` may be another GPU's
+ * memory mapped with rg_shared_frame_open: every GPU of a box then quantises its rows straight
+ * into the one frame on GPU 0 over NVLink / NVSwitch, and `collect` (rendering.rs:34-35) needs no
+ * separate exchange — only a barrier.  Wavefront pipeline only. */
+int rg_render_rowlist_scatter(rg_scene *scene, uint32_t width, uint32_t height,
+                              const uint32_t *rows, uint32_t n_rows, void *d_frame,
+                              void *cuda_stream, rg_stats *stats);
+
+/* A device frame that other PROCESSES (one per GPU) can map: create on the owning rank, pass the
+ * opaque handle bytes to the others (any channel), open there.  Close with is_owner = 1 on the
+ * creating rank (frees the memory), 0 elsewhere (unmaps). */
+#define RG_IPC_HANDLE_BYTES 64u
+int rg_shared_frame_create(int32_t device, size_t bytes, void **d_ptr, uint8_t *handle /* [RG_IPC_HANDLE_BYTES] */);
+int rg_shared_frame_open(int32_t device, const uint8_t *handle, void **d_ptr);
+int rg_shared_frame_close(int32_t device, void *d_ptr, int32_t is_owner);
+
 /* Scene::streaming_render (scene.rs:45-51 -> rendering.rs:40-69): renders in
  * bands of `band_rows` rows (0 = automatic) and hands each finished band to
  * `cb` from the calling thread.  Returns RG_E_CANCELLED if `cb` returned

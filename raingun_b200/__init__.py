@@ -23,7 +23,7 @@ from ._native import (ACCEL_AUTO, ACCEL_BRUTE, ACCEL_GRID, PIPELINE_MEGAKERNEL, 
                       RaingunError)
 from .scene import SceneData, SceneError, Stats, load_scene, parse_scene, scene_from_dict
 
-__all__ = ["Scene", "SceneData", "SceneError", "RaingunError", "Stats", "load_scene", "parse_scene",
+__all__ = ["Scene", "SharedFrame", "SceneData", "SceneError", "RaingunError", "Stats", "load_scene", "parse_scene",
            "scene_from_dict", "device_count", "measure_peaks", "ACCEL_AUTO", "ACCEL_BRUTE", "ACCEL_GRID",
            "PIPELINE_WAVEFRONT", "PIPELINE_MEGAKERNEL"]
 
@@ -37,6 +37,37 @@ def measure_peaks(device: int = 0):
     a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
     _native.check(_native.lib().rg_measure_peaks(device, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
     return a.value, b.value, c.value
+
+
+class SharedFrame:
+    """A device frame on ``device`` that the other ranks of a box map through CUDA IPC and write
+    over NVLink (rg_shared_frame_*).  ``SharedFrame.create`` on the owner, ``handle`` (64 bytes) to
+    the peers by any channel, ``SharedFrame.open`` there."""
+
+    def __init__(self, device: int, ptr: int, nbytes: int, owner: bool, handle: bytes = b"") -> None:
+        self.device, self.ptr, self.nbytes, self.owner, self.handle = device, ptr, nbytes, owner, handle
+
+    @classmethod
+    def create(cls, device: int, nbytes: int) -> "SharedFrame":
+        p = ctypes.c_void_p()
+        h = ctypes.create_string_buffer(_native.IPC_HANDLE_BYTES)
+        _native.check(_native.lib().rg_shared_frame_create(device, nbytes, ctypes.byref(p), h))
+        return cls(device, p.value, nbytes, True, h.raw)
+
+    @classmethod
+    def open(cls, device: int, handle: bytes, nbytes: int) -> "SharedFrame":
+        p = ctypes.c_void_p()
+        _native.check(_native.lib().rg_shared_frame_open(device, handle, ctypes.byref(p)))
+        return cls(device, p.value, nbytes, False, handle)
+
+    @property
+    def __cuda_array_interface__(self):   # zero-copy view for torch.as_tensor(frame, device=...)
+        return {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+
+    def close(self) -> None:
+        if self.ptr:
+            _native.check(_native.lib().rg_shared_frame_close(self.device, ctypes.c_void_p(self.ptr), 1 if self.owner else 0))
+            self.ptr = 0
 
 
 class Scene:
@@ -132,6 +163,18 @@ class Scene:
         st = Stats()
         _native.check(_native.lib().rg_render_rowlist_device(
             self._h, width, height, ctypes.c_void_p(rows.ctypes.data), int(rows.size), ctypes.c_void_p(device_ptr),
+            ctypes.c_void_p(cuda_stream), ctypes.byref(st)))
+        self.last_stats = st
+        return st
+
+    def render_rowlist_scatter(self, width: int, height: int, rows, frame_ptr: int, cuda_stream: int = 0) -> Stats:
+        """As render_rowlist_device, but row ``rows[k]`` lands at its own place in the FULL frame at
+        ``frame_ptr`` — which may be another GPU's memory (``SharedFrame``): the gather of a sharded
+        frame fused into the last kernel."""
+        rows = np.ascontiguousarray(rows, np.uint32)
+        st = Stats()
+        _native.check(_native.lib().rg_render_rowlist_scatter(
+            self._h, width, height, ctypes.c_void_p(rows.ctypes.data), int(rows.size), ctypes.c_void_p(frame_ptr),
             ctypes.c_void_p(cuda_stream), ctypes.byref(st)))
         self.last_stats = st
         return st

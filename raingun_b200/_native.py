@@ -28,8 +28,10 @@ ROWS_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctype
 
 # every symbol include/raingun_b200.h declares
 EXPORTS = ("rg_scene_create", "rg_scene_destroy", "rg_scene_set_option", "rg_render", "rg_render_rows",
-           "rg_render_rows_device", "rg_render_rowlist_device", "rg_render_stream", "rg_last_error", "rg_measure_peaks",
+           "rg_render_rows_device", "rg_render_rowlist_device", "rg_render_rowlist_scatter", "rg_shared_frame_create",
+           "rg_shared_frame_open", "rg_shared_frame_close", "rg_render_stream", "rg_last_error", "rg_measure_peaks",
            "rg_device_count")
+IPC_HANDLE_BYTES = 64
 
 
 class RaingunError(RuntimeError):
@@ -64,6 +66,14 @@ def lib() -> ctypes.CDLL:
     L.rg_render_rows_device.argtypes = [vp, u32, u32, u32, u32, vp, vp, ctypes.POINTER(Stats)]
     L.rg_render_rowlist_device.restype = ctypes.c_int
     L.rg_render_rowlist_device.argtypes = [vp, u32, u32, vp, u32, vp, vp, ctypes.POINTER(Stats)]
+    L.rg_render_rowlist_scatter.restype = ctypes.c_int
+    L.rg_render_rowlist_scatter.argtypes = [vp, u32, u32, vp, u32, vp, vp, ctypes.POINTER(Stats)]
+    L.rg_shared_frame_create.restype = ctypes.c_int
+    L.rg_shared_frame_create.argtypes = [i32, ctypes.c_size_t, ctypes.POINTER(vp), ctypes.c_char_p]
+    L.rg_shared_frame_open.restype = ctypes.c_int
+    L.rg_shared_frame_open.argtypes = [i32, ctypes.c_char_p, ctypes.POINTER(vp)]
+    L.rg_shared_frame_close.restype = ctypes.c_int
+    L.rg_shared_frame_close.argtypes = [i32, vp, i32]
     L.rg_render_stream.restype = ctypes.c_int
     L.rg_render_stream.argtypes = [vp, u32, u32, u32, ROWS_CB, vp, ctypes.POINTER(Stats)]
     L.rg_last_error.restype = ctypes.c_char_p

@@ -70,6 +70,8 @@ void WavefrontScratch::release() {
     sync_events.clear();
     if (aux) cudaStreamDestroy(aux);
     aux = nullptr;
+    if (rb) cudaStreamDestroy(rb);
+    rb = nullptr;
 }
 
 // Scratch arenas outlive a scene: destroying a scene parks its (possibly multi-GB) wavefront
@@ -592,6 +594,51 @@ int rg_render_rowlist_device(rg_scene *sc, uint32_t w, uint32_t h, const uint32_
         RG_CUDA(cudaStreamSynchronize(stream));   // `rows` may be pageable and reused by the caller
     }
     return render_device(sc, w, h, 0, n_rows, sc->rowlist.as<uint32_t>(), d_rgba_out, stream, stats);
+}
+
+int rg_render_rowlist_scatter(rg_scene *sc, uint32_t w, uint32_t h, const uint32_t *rows, uint32_t n_rows,
+                              void *d_frame, void *cuda_stream, rg_stats *stats) {
+    if (sc && sc->pipeline != RG_PIPELINE_WAVEFRONT) { set_error("rg_render_rowlist_scatter needs the wavefront pipeline"); return RG_E_INVALID; }
+    if (!sc) { set_error("scene is NULL"); return RG_E_INVALID; }
+    sc->scatter_out = true;
+    const int rc = rg_render_rowlist_device(sc, w, h, rows, n_rows, d_frame, cuda_stream, stats);
+    sc->scatter_out = false;
+    return rc;
+}
+
+// ---- frames another process' GPU can write into (CUDA IPC; peer stores travel over NVLink) ----
+static_assert(sizeof(cudaIpcMemHandle_t) == RG_IPC_HANDLE_BYTES, "RG_IPC_HANDLE_BYTES");
+
+int rg_shared_frame_create(int32_t device, size_t bytes, void **d_ptr, uint8_t *handle) {
+    if (!d_ptr || !handle || bytes == 0) { set_error("rg_shared_frame_create: bad argument"); return RG_E_INVALID; }
+    RG_CUDA(cudaSetDevice(device));
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaMalloc(shared frame)", __FILE__, __LINE__);
+    cudaIpcMemHandle_t hnd;
+    cudaError_t e = cudaIpcGetMemHandle(&hnd, p);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaIpcGetMemHandle", __FILE__, __LINE__); }
+    std::memcpy(handle, &hnd, sizeof hnd);
+    *d_ptr = p;
+    return RG_OK;
+}
+
+int rg_shared_frame_open(int32_t device, const uint8_t *handle, void **d_ptr) {
+    if (!d_ptr || !handle) { set_error("rg_shared_frame_open: bad argument"); return RG_E_INVALID; }
+    RG_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t hnd;
+    std::memcpy(&hnd, handle, sizeof hnd);
+    void *p = nullptr;
+    RG_CUDA(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+    *d_ptr = p;
+    return RG_OK;
+}
+
+int rg_shared_frame_close(int32_t device, void *d_ptr, int32_t is_owner) {
+    if (!d_ptr) return RG_OK;
+    RG_CUDA(cudaSetDevice(device));
+    if (is_owner) RG_CUDA(cudaFree(d_ptr));
+    else RG_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return RG_OK;
 }
 
 int rg_render_rows(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, uint8_t *rgba_out, rg_stats *stats) {

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
     const GridDev &g = s.grid;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
+    const uint32_t n_rays = a.n_dev ? *a.n_dev : a.n;
     unsigned n_exact = 0, nan_count = 0;
 
     // ---- per-lane ray state
@@ -143,9 +144,9 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(a.fetch, (unsigned)__popc(idle));
             base = __shfl_sync(0xffffffffu, base, 0);
-            exhausted = base + (uint32_t)__popc(idle) >= a.n;
+            exhausted = base + (uint32_t)__popc(idle) >= n_rays;
             const uint32_t ri = base + __popc(idle & lanemask_lt);
-            if (!active && ri < a.n) {
+            if (!active && ri < n_rays) {
                 // ---- set a new ray up: non-sphere bodies, loose spheres, clip to the grid
                 active = true;
                 walking = false;

@@ -56,6 +56,7 @@ struct WavefrontScratch {
     std::vector<DeviceBuffer> nodes;   // per level: NodeA float4 + NodeB uint4
     std::vector<cudaEvent_t> events;   // timing events of the trace launches, reused across frames
     cudaStream_t aux = nullptr;        // shadow-side stream (created on first use)
+    cudaStream_t rb = nullptr;         // counter read-back stream (lets the main stream run ahead of the host)
     std::vector<cudaEvent_t> sync_events;   // cross-stream dependencies (no timing), reused across frames
     void release();
 };
@@ -84,6 +85,7 @@ struct rg_scene {
     uint64_t batch_pixels = 0;
     int verify_cull = 0;
     int overlap = 0;                       // RG_OPT_OVERLAP: 0 auto (on with the grid tracer), 1 off, 2 on
+    bool scatter_out = false;              // this call stores rows at their place in a full frame (rg_render_rowlist_scatter)
     // derived
     uint32_t n_bodies = 0;
     int sm_count = 0;

@@ -42,6 +42,8 @@ struct TraceArgs {
     uint8_t *out_lit;        // ANY: 1 = in light
     DCounters *ctr;
     unsigned int *fetch;     // persistent kernels: the ray counter of THIS launch (ctr->fetch / ctr->fetch_shadow)
+    const unsigned int *n_dev;   // persistent kernels: if set, the ray count is read from device memory (a launch
+                                 // issued before the host knows it; `n` is then only an upper bound)
     int verify;              // RG_OPT_VERIFY_CULL
     int g_refill, g_quorum, g_burst;   // persistent grid kernel tuning (rg_grid.cuh)
 };

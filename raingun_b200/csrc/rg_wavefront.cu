@@ -217,6 +217,31 @@ __global__ void __launch_bounds__(256) k_quantise(const float4 *__restrict__ nod
     }
 }
 
+// The same, fused with the gather of a sharded frame: pixel i of the batch belongs to image row
+// rows[row0 + i / width] and is stored at its place in a FULL frame that may live in another
+// GPU's memory (a CUDA-IPC mapping written over NVLink): the "collective" of this path is these
+// stores, and nothing is left to exchange when the kernel retires.
+__global__ void __launch_bounds__(256) k_quantise_scatter(const float4 *__restrict__ node_a, uchar4 *frame, uint32_t npix,
+                                                          uint32_t width, const uint32_t *__restrict__ rows, uint32_t row0) {
+    const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (i4 >= npix) return;
+    const uint32_t r = i4 / width, x = i4 - r * width;
+    if (x + 4u <= width && i4 + 4u <= npix) {
+        uchar4 *dst = frame + (size_t)rows[row0 + r] * width + x;
+        uchar4 p[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { float4 a = node_a[i4 + k]; p[k] = quantise(c3(a.x, a.y, a.z)); }
+        if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<uint4 *>(p);
+        else { dst[0] = p[0]; dst[1] = p[1]; dst[2] = p[2]; dst[3] = p[3]; }
+    } else {
+        for (uint32_t k = i4; k < npix && k < i4 + 4u; ++k) {
+            const uint32_t rk = k / width;
+            float4 a = node_a[k];
+            frame[(size_t)rows[row0 + rk] * width + (k - rk * width)] = quantise(c3(a.x, a.y, a.z));
+        }
+    }
+}
+
 // RG_OPT_VERIFY_CULL >= 2: re-trace every ray of a queue with the verbatim reference scan and
 // count results that differ from what the production trace kernel wrote (must be 0).
 template <bool ANY>
@@ -338,6 +363,15 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
         aux = wf.aux;
     }
     cudaEvent_t shadow_done[2] = {nullptr, nullptr};   // last shadow-side work that used the parity's buffers
+    // Run-ahead.  The host needs each level's counters (children, lit hits) to size the next
+    // launches, but the persistent grid tracer does not need a launch size: the nearest-hit trace
+    // of level d+1 is enqueued right behind k_shade(d) and reads its ray count from the device
+    // counter k_shade(d) leaves behind.  The counters travel to the host on a third stream, so the
+    // main stream never drains while the host catches up (one level of speculation; a level that
+    // turns out empty costs one no-op launch).
+    const bool run_ahead = overlap && use_grid && sc->verify_cull == 0;
+    if (run_ahead && !wf.rb) RG_CUDA(cudaStreamCreateWithFlags(&wf.rb, cudaStreamNonBlocking));
+    bool traced_ahead = false;   // the nearest trace of the current level is already in the stream
 
     std::vector<uint32_t> level_n;
     uint32_t n = npix, d = 0;
@@ -378,13 +412,15 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
         ta.out_body = wf.hit_body.as<uint32_t>();
         ta.ctr = dc;
         ta.verify = sc->verify_cull == 1;
-        cudaEvent_t e0 = events.get(), e1 = events.get();
-        RG_CUDA(cudaEventRecord(e0, stream));
-        if ((rc = launch_trace<false>(sc, ta, use_grid, stream))) return rc;
-        RG_CUDA(cudaEventRecord(e1, stream));
-        trace_spans.emplace_back(e0, e1);
-        st->gpu_launches++;
-        if (sc->verify_cull >= 2) k_verify_trace<false><<<(n + 127) / 128, 128, 0, stream>>>(ds, ta, (int)d);
+        if (!traced_ahead) {
+            cudaEvent_t e0 = events.get(), e1 = events.get();
+            RG_CUDA(cudaEventRecord(e0, stream));
+            if ((rc = launch_trace<false>(sc, ta, use_grid, stream))) return rc;
+            RG_CUDA(cudaEventRecord(e1, stream));
+            trace_spans.emplace_back(e0, e1);
+            st->gpu_launches++;
+            if (sc->verify_cull >= 2) k_verify_trace<false><<<(n + 127) / 128, 128, 0, stream>>>(ds, ta, (int)d);
+        }
 
         LevelBuffers lb{};
         lb.cur = cur;
@@ -409,8 +445,34 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
         k_shade<<<blocks(n), 256, 0, stream>>>(ds, lb, dc);
         RG_CUDA(cudaGetLastError());
         st->gpu_launches++;
-        RG_CUDA(cudaMemcpyAsync(&hc->q_next, &dc->q_next, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
-        RG_CUDA(cudaStreamSynchronize(stream));
+        traced_ahead = false;
+        cudaStream_t rbs = stream;
+        if (run_ahead) {
+            cudaEvent_t shaded = sync_events.get();
+            RG_CUDA(cudaEventRecord(shaded, stream));
+            if (can_spawn) {   // nearest trace of level d+1, sized on the device (q_next); hits for up to 2n rays
+                if ((rc = wf.hit_t.reserve((size_t)next_cap * 8))) return rc;
+                if ((rc = wf.hit_body.reserve((size_t)next_cap * 4))) return rc;
+                TraceArgs na{};
+                na.q = lb.next;
+                na.n = (uint32_t)next_cap;
+                na.n_dev = &dc->q_next;
+                na.out_t = wf.hit_t.as<double>();
+                na.out_body = wf.hit_body.as<uint32_t>();
+                na.ctr = dc;
+                cudaEvent_t e0 = events.get(), e1 = events.get();
+                RG_CUDA(cudaEventRecord(e0, stream));
+                if ((rc = launch_trace<false>(sc, na, use_grid, stream))) return rc;
+                RG_CUDA(cudaEventRecord(e1, stream));
+                trace_spans.emplace_back(e0, e1);
+                st->gpu_launches++;
+                traced_ahead = true;
+            }
+            rbs = wf.rb;
+            RG_CUDA(cudaStreamWaitEvent(rbs, shaded, 0));
+        }
+        RG_CUDA(cudaMemcpyAsync(&hc->q_next, &dc->q_next, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, rbs));
+        RG_CUDA(cudaStreamSynchronize(rbs));
         const uint32_t n_next = hc->q_next, n_lit = hc->q_lit;
 
         // shadow side: on `aux` (== stream without overlap).  The host has just synchronised the
@@ -462,7 +524,10 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
         RG_CUDA(cudaGetLastError());
         st->gpu_launches++;
     }
-    k_quantise<<<blocks(((uint64_t)npix + 3) / 4), 256, 0, stream>>>(wf.nodes[0].as<float4>(), d_out, npix);
+    if (sc->scatter_out)   // d_out is the base of the whole frame; this batch covers row-list entries [y0, y1)
+        k_quantise_scatter<<<blocks(((uint64_t)npix + 3) / 4), 256, 0, stream>>>(wf.nodes[0].as<float4>(), d_out, npix, width, d_rows, y0);
+    else
+        k_quantise<<<blocks(((uint64_t)npix + 3) / 4), 256, 0, stream>>>(wf.nodes[0].as<float4>(), d_out, npix);
     RG_CUDA(cudaGetLastError());
     st->gpu_launches++;
     st->batches++;
@@ -495,13 +560,14 @@ int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0,
         int rc = RG_OK;
         for (uint32_t y = y0; y < y1 && rc == RG_OK;) {
             const uint32_t ye = (uint32_t)std::min<uint64_t>((uint64_t)y + batch_rows, y1);
-            rc = render_batch(sc, width, height, y, ye, d_rows, d_out + (size_t)(y - y0) * width, stream, st, use_grid,
+            rc = render_batch(sc, width, height, y, ye, d_rows, sc->scatter_out ? d_out : d_out + (size_t)(y - y0) * width, stream, st, use_grid,
                               events, sync_events, trace_spans);
             y = ye;
         }
         if (rc == RG_E_NOMEM && batch_rows > 1) {
             cudaStreamSynchronize(stream);
             if (sc->wf.aux) cudaStreamSynchronize(sc->wf.aux);
+            if (sc->wf.rb) cudaStreamSynchronize(sc->wf.rb);
             sc->wf.release();
             batch_rows = (batch_rows + 1) / 2;
             continue;

@@ -15,6 +15,11 @@ be a list of renderers (one scene handle + CUDA stream each), driven by one host
 static share is split between them and the stealable tail is claimed by whichever thread runs dry,
 so the fixed cost of a small batch hides under the other thread's kernels.
 
+Gather.  ``peer`` (GPUs): rank 0 owns the frame (two, alternating per frame), every other rank
+maps it through CUDA IPC and its last kernel stores each finished row at its place in rank 0's
+memory over NVLink (``rg_render_rowlist_scatter``) — compute and "collective" are one kernel, and a
+barrier is all that is left.  ``reduce`` / ``p2p``: NCCL (or gloo) collectives on packed rows.
+
 One process per GPU (torchrun); works unchanged on the gloo backend with CPU tensors, which
 is how the host logic is tested without GPUs (tests/test_dist_gloo.py).
 """
@@ -133,6 +138,51 @@ class TileCounter:
         return self.chunks[idx] if idx < len(self.chunks) else None
 
 
+class PeerFrames:
+    """Rank 0's frame buffers as every rank of the box sees them (CUDA IPC, written over NVLink).
+    Two frames alternate (``frame_id & 1``): a rank that is already storing rows of frame k+1 cannot
+    disturb rank 0 still reading frame k, and the end-of-frame barrier keeps everyone within one
+    frame of each other."""
+
+    def __init__(self, width: int, height: int, rank: int, world: int, device_index: int, store=None,
+                 tag: str = "0") -> None:
+        from . import SharedFrame
+
+        self.width, self.height, self.rank, self.world, self.device_index = width, height, rank, world, device_index
+        nbytes = width * height * 4
+        self.frames = []
+        for k in range(2):
+            key = f"raingun/peer_frame/{tag}/{k}"
+            if rank == 0:
+                f = SharedFrame.create(device_index, nbytes)
+                if world > 1:
+                    (store or default_store()).set(key, f.handle)
+            else:
+                f = SharedFrame.open(device_index, bytes((store or default_store()).get(key)), nbytes)
+            self.frames.append(f)
+
+    def ptr(self, frame_id: int) -> int:
+        return self.frames[frame_id & 1].ptr
+
+    def tensor(self, frame_id: int) -> torch.Tensor:
+        """Zero-copy (H, W, 4) uint8 view of the frame (meaningful on rank 0, which owns the memory)."""
+        t = torch.as_tensor(self.frames[frame_id & 1], device=torch.device("cuda", self.device_index))
+        return t.view(self.height, self.width, 4)
+
+    def close(self) -> None:
+        if self.world > 1:
+            dist.barrier()   # nobody unmaps or frees while a peer may still be storing
+        for f in self.frames:
+            if not f.owner:
+                f.close()
+        if self.world > 1:
+            dist.barrier()
+        for f in self.frames:
+            if f.owner:
+                f.close()
+        self.frames = []
+
+
 @dataclass
 class ShardResult:
     frame: Optional[torch.Tensor]          # (H, W, 4) uint8 on rank 0, None elsewhere
@@ -152,7 +202,7 @@ def render_frame_sharded(render_rowlist: Union[Callable[[np.ndarray, torch.Tenso
                          tile_rows: int = DEFAULT_TILE_ROWS, schedule: str = "auto",
                          gather: bool = True, staging: Optional[torch.Tensor] = None,
                          gather_mode: str = "reduce", frame_buf: Optional[torch.Tensor] = None,
-                         lead: float = 0.6) -> ShardResult:
+                         lead: float = 0.6, peer_frames: Optional[PeerFrames] = None) -> ShardResult:
     """Renders one frame across ``world`` ranks.
 
     ``render_rowlist(rows, out)`` must fill ``out`` (a uint8 tensor of ``len(rows)*width*4``
@@ -164,7 +214,10 @@ def render_frame_sharded(render_rowlist: Union[Callable[[np.ndarray, torch.Tenso
     ownership only, one batch per rank) or ``"auto"`` (static when every rank owns at least
     ``AUTO_STATIC_MIN_TILES_PER_RANK`` tiles, else steal).
 
-    ``gather_mode``: ``"reduce"`` — every rank scatters its rows into a zeroed full frame and ONE
+    ``gather_mode``: ``"peer"`` — needs ``peer_frames``; the renderers are then called as
+    ``render_rowlist(rows, frame_ptr)`` and must store row ``rows[k]`` at ``frame_ptr + rows[k]*width*4``
+    (``Scene.render_rowlist_scatter``); the frame is complete on rank 0 after one barrier.
+    ``"reduce"`` — every rank scatters its rows into a zeroed full frame and ONE
     NCCL reduce (MAX over disjoint rows, i.e. a gather that needs no ownership exchange) lands the
     frame on rank 0 over NVLink; ``"p2p"`` — the row lists travel through the store and rank 0
     receives each rank's packed rows point to point.
@@ -175,7 +228,10 @@ def render_frame_sharded(render_rowlist: Union[Callable[[np.ndarray, torch.Tenso
     row_bytes = width * 4
     renderers = list(render_rowlist) if isinstance(render_rowlist, (list, tuple)) else [render_rowlist]
     workers = len(renderers)
-    if staging is None:
+    peer = gather_mode == "peer"
+    if peer and peer_frames is None:
+        raise ValueError("gather_mode='peer' needs peer_frames")
+    if staging is None and not peer:
         staging = torch.empty((height * row_bytes,), dtype=torch.uint8, device=device)
     # first[k]: the batch worker k starts with (no counter traffic); claim(): the stealable rest
     if world == 1:
@@ -206,8 +262,11 @@ def render_frame_sharded(render_rowlist: Union[Callable[[np.ndarray, torch.Tenso
                 with lock:   # reserve the output rows of this batch
                     at = state["filled"]
                     state["filled"] = at + int(rows.size)
-                out = staging[at * row_bytes:(at + int(rows.size)) * row_bytes]
-                stat = renderers[k](rows, out)
+                if peer:
+                    stat = renderers[k](rows, peer_frames.ptr(frame_id))
+                else:
+                    out = staging[at * row_bytes:(at + int(rows.size)) * row_bytes]
+                    stat = renderers[k](rows, out)
                 with lock:
                     res.claims += 1
                     res.stats.append(stat)
@@ -225,6 +284,11 @@ def render_frame_sharded(render_rowlist: Union[Callable[[np.ndarray, torch.Tenso
     my_rows = [r for _, r in sorted(my_rows, key=lambda ar: ar[0])]   # staging order
     rows_all = np.concatenate(my_rows) if my_rows else np.zeros(0, np.uint32)
     if not gather:
+        return res
+    if peer:   # the rows are already in rank 0's frame; make that known
+        if world > 1:
+            dist.barrier()
+        res.frame = peer_frames.tensor(frame_id) if rank == 0 else None
         return res
 
     # ---- gather: ownership is dynamic, so the row lists travel first (tiny), then the pixels

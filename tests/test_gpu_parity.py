@@ -126,6 +126,29 @@ def test_streaming_render_bands_and_cancel():
         assert calls == [0]     # cancelled after the first band (closed channel, rendering.rs:53-54,67)
 
 
+def test_scatter_rows_odd_width(oracle):
+    """rg_render_rowlist_scatter with a width that is not a multiple of 4 (scalar store path) and rows in
+    arbitrary order, into a SharedFrame (the buffer other ranks would map through CUDA IPC)."""
+    import torch
+
+    data = example_scene("test2")
+    w, h = 202, 150
+    ref, _, _ = oracle.render(data, w, h)
+    rows = np.array([149, 0, 7, 8, 9, 77, 3], np.uint32)
+    shared = rg.SharedFrame.create(0, w * h * 4)
+    try:
+        view = torch.as_tensor(shared, device="cuda:0").view(h, w, 4)
+        view.zero_()
+        torch.cuda.synchronize()
+        with rg.Scene(data) as sc:
+            sc.render_rowlist_scatter(w, h, rows, shared.ptr, 0)
+        got = view.cpu().numpy()
+    finally:
+        shared.close()
+    assert np.array_equal(got[rows], ref[rows])
+    assert not got[np.setdiff1d(np.arange(h), rows)].any()
+
+
 def test_error_codes():
     data = example_scene("test2")
     with rg.Scene(data) as sc:
@@ -246,6 +269,16 @@ def test_full_size_c4_every_strategy_renders_the_same_frame():
     with rg.Scene(data) as sc:
         sc.render_rowlist_device(w, h, rows, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
     assert np.array_equal(out.cpu().numpy().reshape(rows.size, w, 4), frames["grid"][rows])
+    # the gather-fused form: the same rows stored at their own place in a full frame (two batches)
+    frame = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    with rg.Scene(data) as sc:
+        sc.set_option(rg._native.OPT_BATCH_PIXELS, w * 400)
+        sc.render_rowlist_scatter(w, h, rows, frame.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        assert sc.last_stats.batches == 2
+    got = frame.cpu().numpy()
+    assert np.array_equal(got[rows], frames["grid"][rows])
+    rest = np.setdiff1d(np.arange(h), rows)
+    assert not got[rest].any()
 
 
 def test_full_size_c5_row_matches_oracle(oracle):
