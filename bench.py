@@ -237,9 +237,26 @@ def main() -> int:
         return lanes
 
     peer_frames = None
+    gather_note = None
     if world > 1 and args.gather == "peer":
         from raingun_b200.dist import PeerFrames
-        peer_frames = PeerFrames(w, h, rank, world, local_rank)
+        try:
+            peer_frames = PeerFrames(w, h, rank, world, local_rank)
+        except Exception as e:   # CUDA IPC unavailable (e.g. restricted container): every rank falls back together
+            gather_note = f"peer gather unavailable on rank {rank}: {e}"
+        ok = torch.tensor([0 if peer_frames is None else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if peer_frames is not None and rank != 0:   # importers unmap first ...
+                peer_frames.close(sync=False)
+                peer_frames = None
+            dist.barrier()
+            if peer_frames is not None:                 # ... then the owner frees
+                peer_frames.close(sync=False)
+                peer_frames = None
+            args.gather = "reduce"
+            gather_note = gather_note or "peer gather unavailable on another rank"
+            print(f"[bench] {gather_note}; using the NCCL reduce gather", file=sys.stderr, flush=True)
 
     def lane_renderers(lanes):
         if peer_frames is not None:

@@ -154,11 +154,19 @@ class PeerFrames:
         for k in range(2):
             key = f"raingun/peer_frame/{tag}/{k}"
             if rank == 0:
-                f = SharedFrame.create(device_index, nbytes)
+                try:
+                    f = SharedFrame.create(device_index, nbytes)
+                except Exception:
+                    if world > 1:   # never leave the peers blocked on the key
+                        (store or default_store()).set(key, b"!")
+                    raise
                 if world > 1:
                     (store or default_store()).set(key, f.handle)
             else:
-                f = SharedFrame.open(device_index, bytes((store or default_store()).get(key)), nbytes)
+                handle = bytes((store or default_store()).get(key))
+                if len(handle) != 64:
+                    raise RuntimeError("rank 0 could not create the shared frame")
+                f = SharedFrame.open(device_index, handle, nbytes)
             self.frames.append(f)
 
     def ptr(self, frame_id: int) -> int:
@@ -169,13 +177,15 @@ class PeerFrames:
         t = torch.as_tensor(self.frames[frame_id & 1], device=torch.device("cuda", self.device_index))
         return t.view(self.height, self.width, 4)
 
-    def close(self) -> None:
-        if self.world > 1:
+    def close(self, sync: bool = True) -> None:
+        """``sync=False`` only when no peer can be using the frames (e.g. set-up failed on some rank)."""
+        sync = sync and self.world > 1
+        if sync:
             dist.barrier()   # nobody unmaps or frees while a peer may still be storing
         for f in self.frames:
             if not f.owner:
                 f.close()
-        if self.world > 1:
+        if sync:
             dist.barrier()
         for f in self.frames:
             if f.owner:
