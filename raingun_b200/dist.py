@@ -51,11 +51,24 @@ def tile_rows_range(tile: int, tile_rows: int, height: int) -> range:
     return range(tile * tile_rows, min(height, (tile + 1) * tile_rows))
 
 
+_ROWS_CACHE: dict = {}
+
+
 def rows_of_tiles(tiles: Sequence[int], tile_rows: int, height: int) -> np.ndarray:
+    """Image rows of the listed tiles, in list order (read-only array: static shares repeat every
+    frame, so the result is memoised)."""
     if len(tiles) == 0:
         return np.zeros(0, np.uint32)
-    return np.concatenate([np.arange(r.start, r.stop, dtype=np.uint32)
-                           for r in (tile_rows_range(t, tile_rows, height) for t in tiles)])
+    key = (tuple(tiles), tile_rows, height)
+    rows = _ROWS_CACHE.get(key)
+    if rows is None:
+        if len(_ROWS_CACHE) > 256:
+            _ROWS_CACHE.clear()
+        rows = np.concatenate([np.arange(r.start, r.stop, dtype=np.uint32)
+                               for r in (tile_rows_range(t, tile_rows, height) for t in tiles)])
+        rows.setflags(write=False)
+        _ROWS_CACHE[key] = rows
+    return rows
 
 
 def resolve_schedule(schedule: str, num_tiles: int, world: int) -> str:
