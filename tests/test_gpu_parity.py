@@ -289,3 +289,28 @@ def test_full_size_c5_row_matches_oracle(oracle):
     y = 2600
     ref, _, _ = oracle.render_rows(data, spec.width, spec.height, y, y + 1)
     assert np.array_equal(img[y:y + 1], ref)
+
+
+def test_degenerate_scenes(oracle):
+    """Edge cases of the level loop: no lights (no shadow side at all), no bodies (every pixel is
+    default_color after one traced primary ray, rendering.rs:71-78), a single level."""
+    import copy
+    from raingun_b200.scene import scene_from_dict
+    from raingun_b200.synth import SPECS, make_scene_doc
+
+    base = make_scene_doc(SPECS["C4"], spheres=150, depth=5)
+    no_lights = copy.deepcopy(base)
+    no_lights["lights"] = []
+    no_bodies = copy.deepcopy(base)
+    no_bodies["bodies"] = []
+    one_level = copy.deepcopy(base)
+    one_level["maxRecursionDepth"] = 1
+    for label, doc in (("no lights", no_lights), ("no bodies", no_bodies), ("one level", one_level)):
+        data = scene_from_dict(doc)
+        ref, ost, _ = oracle.render(data, 160, 90)
+        for mode in MODES:
+            img, st = _render(data, 160, 90, mode[1], mode[2])
+            _assert_same(img, ref, st, ost, f"{label}/{mode[0]}")
+    data = scene_from_dict(no_bodies)
+    img, st = _render(data, 160, 90, rg.PIPELINE_WAVEFRONT, rg.ACCEL_AUTO)
+    assert st.rays == 160 * 90 and (img[..., :3] == np.array([0x66, 0x7f, 0xff], np.uint8)).all()
