@@ -48,6 +48,22 @@ def workload_config(name, spec, data, extra):
     return cfg
 
 
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's first launch (level-0
+    nearest-hit k_trace_brute: 8.29 M rays) from the committed `ncu --set full` capture, per launch;
+    None when no summary is present.  Not measured in this run: ncu cannot run inside the bench."""
+    import glob
+    import re
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_summary.md")), reverse=True):
+        text = open(path).read()
+        m = re.search(r"capture `prof_brute_r\w+\.ncu-rep`.*?k_trace_brute<0.*?DRAM read: ([\d.]+) (M|G)byte.*?DRAM written: ([\d.]+) (M|G)byte",
+                      text, re.S)
+        if m:
+            unit = {"M": 1e6, "G": 1e9}
+            return int(float(m.group(1)) * unit[m.group(2)] + float(m.group(3)) * unit[m.group(4)]), os.path.basename(path)
+    return None, None
+
+
 class ClockSampler:
     """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -379,10 +395,13 @@ def main() -> int:
                 blaunch += 2 * (st.max_level + 1)
             sc.close()
             fl = flops_per_ray(data)
+            traffic, traffic_src = profiled_traffic()
             achieved = brays * fl / (tr_ms * 1e-3) / 1e12
             roofline = {"bound": "fp32", "kernel": "k_trace_brute (nearest + shadow variants), accel=brute",
                         "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                        "traffic": None,
+                        "traffic": traffic, "traffic_source": traffic_src and
+                        f"profiles/{traffic_src}: DRAM read + written by the level-0 nearest-hit launch (8.29 M rays; algorithmic 60 B/ray "
+                        "= 48 B ray + 12 B hit = 498 MB) - the kernel re-reads nothing from HBM",
                         "algorithmic_flops_per_ray": fl,
                         "pair_tests_per_s": brays * float(data.n_bodies) / (tr_ms * 1e-3),
                         "peak_source": "rg_measure_peaks: register-resident FFMA loop on this GPU, this run (MEASURED_PEAKS.json "
