@@ -371,4 +371,230 @@ k_trace_brute(const DScene s, const TraceArgs a) {
     }
 }
 
+// ---- the same scan with the WHOLE cull array resident in shared memory ----------------------
+// When every sphere's 16-byte cull record fits in one SM's shared memory (<= ~11,000 spheres in
+// the 227 KB a CTA may use), the chunk pipeline above is unnecessary — and so is its block-wide
+// barrier per chunk, which is where the streaming kernel loses its time on incoherent bounces
+// (warps whose rays produce more exact tests arrive late; ncu: barrier = 24 % of the stall
+// samples of a deep level, 2.9 % at level 0).  Here one persistent 1024-thread CTA per SM loads the
+// array ONCE (bulk async copies on one mbarrier), after which its 32 warps never synchronise with
+// each other again: each warp pulls tiles of 32*R rays from a global counter, scans all records,
+// evaluates its own survivors and writes its own results.  The arithmetic and the survivor logic
+// are the streaming kernel's, so results are identical.
+// dynamic shared memory: records (+ slack) | per-warp best_t, best_b, cq, tag
+__host__ __device__ inline size_t resident_smem_bytes(uint32_t n_records, int R, int warps) {
+    const size_t rec = ((size_t)n_records + kCullPad) * 16;
+    const size_t per_warp = (size_t)32 * R * (8 + 4 + 1) + 64 * 4;
+    return rec + (size_t)warps * ((per_warp + 15) & ~(size_t)15) + 16;
+}
+
+// T threads per CTA (one CTA per SM); PF = software prefetch of the next U records (costs U float4 of registers)
+template <bool ANY, int R, int U, int T, bool PF>
+__global__ void __launch_bounds__(T, 1)
+k_trace_brute_resident(const DScene s, const TraceArgs a, const uint32_t n_records) {
+    static_assert(U == 2 || U == 4, "U spheres = U/2 pairs per iteration");
+    static_assert(32 * R <= (1 << kSlotBits), "slot bits");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t mbar;
+    float4 *stage = reinterpret_cast<float4 *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr size_t kPerWarp = (((size_t)32 * R * (8 + 4 + 1) + 64 * 4) + 15) & ~(size_t)15;
+    unsigned char *mine = smem_raw + ((size_t)n_records + kCullPad) * 16 + (size_t)warp * kPerWarp;
+    double *best_t = reinterpret_cast<double *>(mine);                        // [32 R]
+    uint32_t *best_b = reinterpret_cast<uint32_t *>(mine + 32 * R * 8);       // [32 R] nearest: body; ANY: 1 = occluded
+    uint32_t *cq = reinterpret_cast<uint32_t *>(mine + 32 * R * 12);          // [64]
+    uint8_t *tag = reinterpret_cast<uint8_t *>(mine + 32 * R * 12 + 64 * 4);  // [32 R]
+
+    const uint32_t lanemask_lt = (1u << lane) - 1u;
+    const uint32_t nsph = s.n_spheres;
+    const uint32_t n_rays = a.n;
+    unsigned long long n_exact = 0;
+    unsigned nan_count = 0, unsound = 0;
+
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t total = n_records * 16u;
+        mbar_expect_tx(&mbar, total);
+        for (uint32_t off = 0; off < total; off += 16384u) {
+            const uint32_t bytes = total - off < 16384u ? total - off : 16384u;
+            bulk_g2s(reinterpret_cast<unsigned char *>(stage) + off, reinterpret_cast<const unsigned char *>(s.cull2) + off, bytes, &mbar);
+        }
+    }
+    __syncthreads();          // the barrier is initialised before anyone waits on it
+    mbar_wait(&mbar, 0u);     // ... and this is the last time the warps of this CTA meet
+    const float4 *sp = stage;
+    const uint32_t cnt = n_records;
+
+    for (;;) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(a.fetch, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        const uint64_t base64 = (uint64_t)tile * (32u * R);
+        if (base64 >= n_rays) break;
+        const uint32_t tile_base = (uint32_t)base64;
+
+        // ---- prologue: my R rays; the few non-sphere bodies are tested exactly right here
+        CullRay2 cr[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t slot = r * 32 + lane;
+            const uint32_t i = tile_base + slot;
+            const bool active = i < n_rays;
+            Ray ray;
+            ray.o = d3(0, 0, 0);
+            ray.d = d3(0, 0, 0);
+            const uint32_t pi = active ? phys_index(a, i) : 0u;
+            if (active) ray = load_ray(a.q, pi);
+            cr[r] = make_cull_ray2(make_cull_ray(s, ray, active));
+            Nearest best;
+            best.init();
+            bool occluded = false;
+            if (active) {
+                const double tmax = ANY ? a.tmax[pi] : 0.0;
+                for (uint32_t m = 0; m < s.n_misc; ++m) {
+                    uint32_t b = s.misc_body[m];
+                    double t;
+                    if (misc_intersect(s, b, ray, t)) {
+                        if (t != t) { ++nan_count; continue; }
+                        if (ANY) occluded = occluded || (t <= tmax);
+                        else best.offer(t, b);
+                    }
+                }
+                n_exact += s.n_misc;
+            }
+            best_t[slot] = best.t;
+            best_b[slot] = ANY ? (occluded ? 1u : 0u) : best.body;
+        }
+        __syncwarp();
+        uint32_t qn = 0;   // warp-uniform: candidates waiting in cq
+
+        // Evaluates candidates cq[first .. first+count) — one per lane — exactly.
+        auto drain = [&](uint32_t first, uint32_t count) {
+            bool have = (uint32_t)lane < count;
+            uint32_t slot = 0, sph = 0;
+            bool hit = false;
+            double t = 0.0;
+            if (have) {
+                uint32_t e = cq[first + lane];
+                slot = e & ((1u << kSlotBits) - 1u);
+                sph = e >> kSlotBits;
+                Ray ray = load_ray(a.q, phys_index(a, tile_base + slot));
+                double4 e4 = s.sph[sph];
+                hit = sphere_intersect(e4.x, e4.y, e4.z, e4.w, ray, t);
+                ++n_exact;
+                if (hit && t != t) { ++nan_count; hit = false; }
+            }
+            if (ANY) {
+                if (hit && t <= a.tmax[phys_index(a, tile_base + slot)]) best_b[slot] = 1u;   // benign race: all write 1
+            } else {
+                const uint32_t body = hit ? s.sph_body[sph] : 0u;
+                bool pend = hit;
+                while (__any_sync(0xffffffffu, pend)) {      // serialise candidates of the same ray
+                    if (pend) tag[slot] = (uint8_t)lane;
+                    __syncwarp();
+                    if (pend && tag[slot] == (uint8_t)lane) {
+                        Nearest cur;
+                        cur.t = best_t[slot];
+                        cur.body = best_b[slot];
+                        cur.offer(t, body);
+                        best_t[slot] = cur.t;
+                        best_b[slot] = cur.body;
+                        pend = false;
+                    }
+                    __syncwarp();
+                }
+            }
+        };
+        // Rare path for the group of U records starting at j0 (see k_trace_brute).
+        auto survivors = [&](uint32_t j0) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t sph = j0 + u;
+                const float4 A = sp[(j0 + u) & ~1u], B = sp[((j0 + u) & ~1u) + 1];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t slot = r * 32 + lane;
+                    const bool live = (tile_base + slot < n_rays) && sph < nsph;
+                    const bool rej = cull_reject_half(cr[r], A, B, (j0 + u) & 1);
+                    const bool pass = live && !rej;
+                    if (a.verify && live && rej) {   // debug: a culled pair must miss exactly
+                        Ray ray = load_ray(a.q, phys_index(a, tile_base + slot));
+                        double4 e = s.sph[sph];
+                        double t;
+                        if (sphere_intersect(e.x, e.y, e.z, e.w, ray, t)) ++unsound;
+                    }
+                    const uint32_t mask = __ballot_sync(0xffffffffu, pass);
+                    if (mask) {
+                        if (pass) cq[qn + __popc(mask & lanemask_lt)] = (sph << kSlotBits) | slot;
+                        qn += __popc(mask);
+                        __syncwarp();
+                        if (qn >= 32u) {
+                            drain(qn - 32u, 32u);
+                            qn -= 32u;
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+        };
+        // Hot loop: identical to the streaming kernel's, over the whole array.
+        float4 sv[U];
+        if (PF) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) sv[u] = sp[u];
+        }
+        bool prev_pass = false;
+#pragma unroll 1
+        for (uint32_t j = 0; j < cnt; j += U) {
+            float4 sc[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) sc[u] = PF ? sv[u] : sp[j + u];
+            if (PF) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) sv[u] = sp[j + U + u];   // software prefetch (kCullPad records of slack)
+            }
+            const bool vote_prev = __any_sync(0xffffffffu, prev_pass);
+            bool any_pass = a.verify != 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                for (int u = 0; u < U; u += 2) {
+                    const float2 h = cull_h2(cr[r], sc[u], sc[u + 1]);
+                    any_pass = any_pass | !(h.x < cr[r].nthr) | !(h.y < cr[r].nthr);
+                }
+            }
+            if (vote_prev) survivors(j - U);
+            prev_pass = any_pass;
+        }
+        if (cnt && __any_sync(0xffffffffu, prev_pass)) survivors(cnt - U);
+        if (qn) drain(0u, qn);
+        __syncwarp();
+
+        // ---- epilogue of the tile
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t slot = r * 32 + lane;
+            const uint32_t i = tile_base + slot;
+            if (i < n_rays) {
+                const uint32_t pi = phys_index(a, i);
+                if (ANY) a.out_lit[pi] = best_b[slot] ? 0 : 1;
+                else { a.out_t[pi] = best_t[slot]; a.out_body[pi] = best_b[slot]; }
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o);
+        nan_count += __shfl_xor_sync(0xffffffffu, nan_count, o);
+        unsound += __shfl_xor_sync(0xffffffffu, unsound, o);
+    }
+    if (lane == 0) {
+        if (n_exact) atomicAdd(&a.ctr->exact_tests, n_exact);
+        if (nan_count) atomicAdd(&a.ctr->err_nan, (unsigned long long)nan_count);
+        if (unsound) atomicAdd(&a.ctr->cull_unsound, (unsigned long long)unsound);
+    }
+}
+
 }  // namespace rg

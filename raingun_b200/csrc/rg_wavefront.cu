@@ -290,6 +290,17 @@ struct EventPool {
     }
 };
 
+constexpr int kResidentSmemMax = 232448 - 1024;   // opt-in shared memory of one CTA on sm_100 (227 KB), minus the static part
+
+// Can k_trace_brute_resident hold this scene's cull records (plus its per-warp scratch) in the
+// shared memory one CTA may use?  (RG_BRUTE_RESIDENT=0 forces the streaming kernel.)
+static bool brute_resident_fits(const rg_scene *sc) {
+    static const bool enabled = [] { const char *e = getenv("RG_BRUTE_RESIDENT"); return !e || atoi(e) != 0; }();
+    if (!enabled || sc->ds.n_spheres == 0) return false;
+    const uint32_t n_records = (uint32_t)(((size_t)sc->ds.n_spheres + 3) / 4 * 4);
+    return resident_smem_bytes(n_records, 4, 20) <= (size_t)kResidentSmemMax;
+}
+
 template <bool ANY>
 static int launch_trace(rg_scene *sc, const TraceArgs &ta, bool use_grid, cudaStream_t stream) {
     if (ta.n == 0) return RG_OK;
@@ -306,6 +317,35 @@ static int launch_trace(rg_scene *sc, const TraceArgs &ta, bool use_grid, cudaSt
         tuned.fetch = ANY ? &ta.ctr->fetch_shadow : &ta.ctr->fetch;   // the two kinds may run concurrently
         RG_CUDA(cudaMemsetAsync(tuned.fetch, 0, sizeof(unsigned int), stream));
         k_trace_grid<ANY><<<blocks, kGridTraceThreads, 0, stream>>>(sc->ds, tuned);
+    } else if (brute_resident_fits(sc) && ta.n >= (uint32_t)sc->sm_count * 64u * 32u) {
+        // the whole cull array fits in one SM's shared memory: one persistent CTA per SM, warps
+        // pull ray tiles from a counter and never meet at a barrier again (rg_trace.cuh)
+        static const int variant = [] { const char *e = getenv("RG_RESIDENT_VARIANT"); return e ? atoi(e) : 0; }();
+        const uint32_t n_records = (uint32_t)(((size_t)sc->ds.n_spheres + 3) / 4 * 4);
+        TraceArgs tuned = ta;
+        tuned.fetch = ANY ? &ta.ctr->fetch_shadow : &ta.ctr->fetch;
+        RG_CUDA(cudaMemsetAsync(tuned.fetch, 0, sizeof(unsigned int), stream));
+#define RG_LAUNCH_RESIDENT(R_, U_, T_, PF_)                                                                                   \
+    do {                                                                                                                      \
+        static bool attr_set = false;                                                                                         \
+        if (!attr_set) {                                                                                                      \
+            RG_CUDA(cudaFuncSetAttribute(k_trace_brute_resident<ANY, R_, U_, T_, PF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         kResidentSmemMax));                                                                  \
+            attr_set = true;                                                                                                  \
+        }                                                                                                                     \
+        const uint64_t tiles = ((uint64_t)ta.n + 32 * R_ - 1) / (32 * R_);                                                     \
+        const unsigned blocks = (unsigned)std::min<uint64_t>((uint64_t)sc->sm_count, (tiles + (T_ / 32) - 1) / (T_ / 32));      \
+        k_trace_brute_resident<ANY, R_, U_, T_, PF_><<<blocks, T_, resident_smem_bytes(n_records, R_, T_ / 32), stream>>>(sc->ds, tuned, n_records); \
+    } while (0)
+        // measured on C4 (ms of trace kernels per 4K frame; streaming kernel 394.7): R=3,U=2,640 thr 356.0;
+        // R=4,U=2,512 thr 360.7; R=2,U=4,512 thr 379.5; R=2,U=4,1024 thr (64 registers, spills) 409;
+        // R=6,U=2,384 thr 408.8; R=8,U=2,256 thr 559 — register tiling pays until too few warps are left
+        switch (variant) {
+            case 1: RG_LAUNCH_RESIDENT(4, 2, 512, true); break;
+            case 2: RG_LAUNCH_RESIDENT(2, 4, 512, true); break;
+            default: RG_LAUNCH_RESIDENT(3, 2, 640, true); break;
+        }
+#undef RG_LAUNCH_RESIDENT
     } else {
         // register tiling R: 4 rays per thread when there is enough work to fill the chip
         const uint64_t full = (uint64_t)sc->sm_count * 2 * kTraceThreads;

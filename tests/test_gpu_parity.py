@@ -281,6 +281,18 @@ def test_full_size_c4_every_strategy_renders_the_same_frame():
     assert not got[rest].any()
 
 
+def test_resident_brute_kernel_cull_is_sound_at_scale():
+    """The shared-memory-resident brute-force kernel (queues of >= 300 k rays, scenes of <= ~11,000
+    spheres) with RG_OPT_VERIFY_CULL=1: every pair the FP32 cull rejects is re-tested exactly on the
+    device and must miss; the image must equal the grid tracer's."""
+    data, _ = make_scene("C3")
+    w, h = 1920, 1080
+    img, st = _render(data, w, h, rg.PIPELINE_WAVEFRONT, rg.ACCEL_BRUTE, verify=True)
+    assert st.cull_unsound == 0 and st.rays_primary == w * h
+    ref, rst = _render(data, w, h, rg.PIPELINE_WAVEFRONT, rg.ACCEL_GRID)
+    assert np.array_equal(img, ref) and st.rays == rst.rays
+
+
 def test_full_size_c5_row_matches_oracle(oracle):
     """configs[4]: 7680x4320, 100,000 spheres, 4 spherical lights, textured, depth 8 (two wavefront
     batches).  One full-resolution row through the oracle (~1.7e10 body tests) pins it."""
