@@ -56,7 +56,7 @@ def profiled_traffic():
     import re
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_summary.md")), reverse=True):
         text = open(path).read()
-        m = re.search(r"capture `prof_brute_r\w+\.ncu-rep`.*?k_trace_brute<0.*?DRAM read: ([\d.]+) (M|G)byte.*?DRAM written: ([\d.]+) (M|G)byte",
+        m = re.search(r"capture `prof_brute_r\w+\.ncu-rep`.*?k_trace_brute(?:_resident)?<0.*?DRAM read: ([\d.]+) (M|G)byte.*?DRAM written: ([\d.]+) (M|G)byte",
                       text, re.S)
         if m:
             unit = {"M": 1e6, "G": 1e9}
@@ -397,7 +397,7 @@ def main() -> int:
             fl = flops_per_ray(data)
             traffic, traffic_src = profiled_traffic()
             achieved = brays * fl / (tr_ms * 1e-3) / 1e12
-            roofline = {"bound": "fp32", "kernel": "k_trace_brute (nearest + shadow variants), accel=brute",
+            roofline = {"bound": "fp32", "kernel": "k_trace_brute_resident / k_trace_brute (nearest + shadow variants), accel=brute",
                         "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                         "traffic": traffic, "traffic_source": traffic_src and
                         f"profiles/{traffic_src}: DRAM read + written by the level-0 nearest-hit launch (8.29 M rays; algorithmic 60 B/ray "

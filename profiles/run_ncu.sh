@@ -23,8 +23,11 @@ $CMD > /dev/null 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_trace_brute -s 14 -c 2 \
     -o gpurun_out/prof_brute_deep_${TAG} -f $CMD > gpurun_out/ncu_brute_deep_${TAG}.log 2>&1
 echo "deep brute capture rc=$?"
+if [ "${SKIP_SHADE:-0}" = "0" ]; then   # gpurun copies back at most 64 MiB: SKIP_SHADE=1 when the reports get large
 $CMD > /dev/null 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_shade -s 9 -c 1 \
     -o gpurun_out/prof_shade_${TAG} -f $CMD > gpurun_out/ncu_shade_${TAG}.log 2>&1
 echo "shade capture rc=$?"
+fi
+du -sh gpurun_out
 ls -la gpurun_out/
