@@ -81,3 +81,39 @@ def test_product_does_not_touch_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "raingun_oracle" not in text and "from oracle" not in text and "import oracle" not in text, \
                     os.path.join(dirpath, f)
+
+
+def test_headers_are_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: both headers must compile as C99 (no C++-isms, no torch or
+    CUDA types in the signatures) and a C program must link against the libraries' entry points."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    inc = os.path.join(ROOT, "include")
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include "raingun_b200.h"\n#include "raingun_host.h"\n'
+        "int main(void) {\n"
+        "    rg_scene_desc d; rg_stats s; rgh_image im; rgh_cli_options o; rg_scene *sc = 0; rgh_scene *hs = 0;\n"
+        "    (void)d; (void)s; (void)im; (void)o;\n"
+        "    /* take the address of every entry point a host would bind */\n"
+        "    void *fns[] = {(void *)rg_scene_create, (void *)rg_scene_destroy, (void *)rg_scene_set_option, (void *)rg_render,\n"
+        "                   (void *)rg_render_rows, (void *)rg_render_rows_device, (void *)rg_render_rowlist_device,\n"
+        "                   (void *)rg_render_rowlist_scatter, (void *)rg_shared_frame_create, (void *)rg_shared_frame_open,\n"
+        "                   (void *)rg_shared_frame_close, (void *)rg_render_stream, (void *)rg_last_error, (void *)rg_device_count,\n"
+        "                   (void *)rgh_scene_load, (void *)rgh_scene_parse, (void *)rgh_scene_desc, (void *)rgh_scene_destroy,\n"
+        "                   (void *)rgh_jpeg_decode, (void *)rgh_png_decode, (void *)rgh_png_encode, (void *)rgh_image_open,\n"
+        "                   (void *)rgh_png_save, (void *)rgh_cli_parse, (void *)rgh_last_error, (void *)rgh_free};\n"
+        "    (void)sc; (void)hs;\n"
+        "    return rg_device_count() < 0 || sizeof(fns) == 0;\n"
+        "}\n")
+    pkg = os.path.join(ROOT, "raingun_b200")
+    exe = tmp_path / "abi"
+    r = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-Wno-pedantic", "-I", inc, str(src), "-o", str(exe),
+                        "-L", pkg, "-lraingun_b200", "-lraingun_host", f"-Wl,-rpath,{pkg}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr   # rg_device_count() is 0 without a GPU, never negative
