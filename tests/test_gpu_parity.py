@@ -326,3 +326,129 @@ def test_degenerate_scenes(oracle):
     data = scene_from_dict(no_bodies)
     img, st = _render(data, 160, 90, rg.PIPELINE_WAVEFRONT, rg.ACCEL_AUTO)
     assert st.rays == 160 * 90 and (img[..., :3] == np.array([0x66, 0x7f, 0xff], np.uint8)).all()
+
+
+# ------------------------------------------------------------------ adversarial geometry
+def _mat(rng, kind=None, tex=None):
+    kind = kind or rng.choice(["Diffuse", "Reflecting", "Refractive"], p=[0.4, 0.3, 0.3])
+    surface = "Diffuse"
+    if kind == "Reflecting":
+        surface = {"Reflecting": {"reflectivity": float(np.round(rng.uniform(0.1, 1.0), 3))}}
+    elif kind == "Refractive":
+        surface = {"Refractive": {"index": float(np.round(rng.uniform(1.0, 2.4), 3)),
+                                  "transparency": float(np.round(rng.uniform(0.0, 1.0), 3))}}
+    col = {"Color": "#%06x" % int(rng.integers(0, 1 << 24))}
+    if tex is not None:
+        col = {"Texture": {"image": tex, "x_offset": float(np.round(rng.uniform(-2, 2), 3)),
+                           "y_offset": float(np.round(rng.uniform(-2, 2), 3))}}
+    return {"coloration": col, "albedo": float(np.round(rng.uniform(0.05, 1.0), 3)), "surface": surface}
+
+
+def _sphere(rng, c, r, **kw):
+    return {"Sphere": {"center": [float(x) for x in c], "radius": float(r), "material": _mat(rng, **kw)}}
+
+
+def _adversarial_scenes():
+    from raingun_b200.synth import CLAY, EARTH
+
+    out = []
+    sun = {"Directional": {"direction": [0.0, -1.0, 0.0], "color": "#ffffff", "intensity": 5.0}}   # axis-parallel shadow rays
+    bulb = lambda p, i=3000.0: {"Spherical": {"position": [float(x) for x in p], "color": "#ffeedd", "intensity": i}}
+    ground = lambda rng, **kw: {"Plane": {"origin": [0.0, -2.0, 0.0], "normal": [0.0, -1.0, 0.0], "material": _mat(rng, **kw)}}
+
+    rng = np.random.default_rng(11)   # A: the camera sits inside a big refractive sphere
+    bodies = [ground(rng, kind="Diffuse"), _sphere(rng, (0, 0, -1), 6.0, kind="Refractive")]
+    bodies += [_sphere(rng, rng.uniform((-4, -1.5, -9), (4, 4, -2)), rng.uniform(0.1, 0.6)) for _ in range(40)]
+    out.append(("camera-inside-glass", {"maxRecursionDepth": 6, "lights": [sun, bulb((2, 3, -3))], "bodies": bodies}))
+
+    rng = np.random.default_rng(12)   # B: integer lattice, radii that touch cell walls, axis-parallel light
+    bodies = [ground(rng, kind="Reflecting")]
+    bodies += [_sphere(rng, (x, y, z), 0.5) for x in range(-3, 4) for y in range(-1, 3) for z in range(-10, -3)]
+    out.append(("lattice", {"maxRecursionDepth": 5, "fov": 70.0, "lights": [sun, bulb((0, 6, -6))], "bodies": bodies}))
+
+    rng = np.random.default_rng(13)   # C: dense overlapping cluster, one huge ("loose") sphere, specks
+    bodies = [_sphere(rng, (0, -60, -20), 55.0, kind="Diffuse")]
+    bodies += [_sphere(rng, rng.normal((0, 0, -8), 1.2), rng.uniform(0.2, 1.0)) for _ in range(120)]
+    bodies += [_sphere(rng, rng.uniform((-3, -2, -7), (3, 3, -3)), rng.uniform(1e-3, 2e-2)) for _ in range(150)]
+    out.append(("cluster+loose+specks", {"maxRecursionDepth": 7, "lights": [bulb((0, 8, -4)), bulb((-6, 1, -2), 800.0)],
+                                        "bodies": bodies}))
+
+    rng = np.random.default_rng(14)   # D: disks, boxes and textures among enough spheres to enable the grid
+    bodies = [ground(rng, tex=CLAY),
+              {"Disk": {"origin": [1.5, 0.5, -6.0], "normal": [0.3, -0.2, -1.0], "radius": 1.8, "material": _mat(rng, kind="Reflecting")}},
+              {"Disk": {"origin": [-2.0, 1.0, -5.0], "normal": [0.0, 0.0, -2.5], "radius": 1.0, "material": _mat(rng, tex=EARTH)}},
+              {"AABB": {"bounds": [[-3.5, -2.0, -9.0], [-1.5, 0.5, -7.0]], "material": _mat(rng, kind="Diffuse")}},
+              {"AABB": {"bounds": [[1.0, -2.0, -4.5], [2.0, -1.0, -3.5]], "material": _mat(rng, kind="Reflecting")}}]
+    bodies += [_sphere(rng, rng.uniform((-5, -1.5, -12), (5, 5, -3)), rng.uniform(0.15, 0.7),
+                       tex=(EARTH if i % 3 == 0 else None)) for i in range(90)]
+    out.append(("mixed-kinds+textures", {"maxRecursionDepth": 6, "defaultColor": "#203040",
+                                         "lights": [sun, bulb((3, 5, -2)), bulb((-4, 2, -10), 1500.0)], "bodies": bodies}))
+
+    rng = np.random.default_rng(15)   # E: far-away geometry (FP32 grid coordinates would fail) and horizon hits
+    bodies = [ground(rng, kind="Reflecting")]
+    bodies += [_sphere(rng, rng.uniform((-400, 0, -3000), (400, 600, -800)), rng.uniform(20, 90)) for _ in range(80)]
+    out.append(("far-field", {"maxRecursionDepth": 5, "fov": 40.0,
+                              "lights": [{"Directional": {"direction": [0.3, -1.0, -0.2], "color": "#ffffff", "intensity": 4.0}},
+                                         bulb((0, 900, -1500), 4e7)], "bodies": bodies}))
+
+    rng = np.random.default_rng(16)   # F: lights inside bodies / at a centre / with zero intensity; 12 spheres (grid only if forced)
+    bodies = [ground(rng, kind="Diffuse")] + [_sphere(rng, rng.uniform((-3, -1, -8), (3, 3, -3)), rng.uniform(0.4, 1.2)) for _ in range(12)]
+    c0 = bodies[1]["Sphere"]["center"]
+    out.append(("odd-lights", {"maxRecursionDepth": 4, "lights": [bulb(c0, 500.0), bulb((0, 1, -5), 0.0), sun], "bodies": bodies}))
+
+    rng = np.random.default_rng(17)   # G: degenerate parameters the reference accepts without complaint
+    bodies = [ground(rng, kind="Diffuse"),
+              _sphere(rng, (0, 0, 0), 0.75, kind="Refractive"),          # centred on the camera: h = 0
+              _sphere(rng, (1, 0, -4), 0.0), _sphere(rng, (-1, 0.5, -4), -0.6, kind="Reflecting"),   # zero / negative radius
+              {"Plane": {"origin": [0, 0, -9], "normal": [0.0, 0.0, 0.0], "material": _mat(rng)}},     # den = 0: never hit
+              {"Disk": {"origin": [0, 1, -5], "normal": [0, 0, -1], "radius": 0.0, "material": _mat(rng)}},
+              {"AABB": {"bounds": [[1.0, 1.0, -5.0], [-1.0, -1.0, -7.0]], "material": _mat(rng, kind="Diffuse")}},   # min > max
+              {"AABB": {"bounds": [[2.0, -2.0, -6.0], [2.0, 0.0, -4.0]], "material": _mat(rng, kind="Diffuse")}}]    # zero thickness
+    bodies += [_sphere(rng, rng.uniform((-4, -1.5, -10), (4, 4, -2)), rng.uniform(-0.5, 0.9)) for _ in range(30)]
+    out.append(("degenerate-parameters", {"maxRecursionDepth": 6, "fov": 150.0, "lights": [sun, bulb((0, 0, 0), 200.0)],
+                                          "bodies": bodies}))
+    return out
+
+
+@pytest.mark.parametrize("case", _adversarial_scenes(), ids=lambda c: c[0])
+def test_adversarial_geometry_matches_oracle(oracle, case):
+    """Scenes built to stress what the synthetic configs do not: origins inside spheres, rays parallel
+    to grid axes and through cell corners, a sphere too large for the grid, specks, every body kind,
+    far-away coordinates, lights inside geometry.  Every pipeline, byte for byte, equal ray counts and
+    equal panic counters (NaN distances, failed transmissions, undecidable box normals)."""
+    from raingun_b200.scene import scene_from_dict
+
+    name, doc = case
+    data = scene_from_dict(doc, bundled_texture_loader)
+    w, h = 224, 126
+    ref, ost, _ = oracle.render(data, w, h)
+    for mode in MODES:
+        img, st = _render(data, w, h, mode[1], mode[2], verify=(mode[0] == "wavefront-brute"))
+        _assert_same(img, ref, st, ost, f"{name}/{mode[0]}")
+        assert st.cull_unsound == 0
+
+
+def test_reference_panic_conditions_are_counted_not_raised(oracle):
+    """Where the reference would panic, the library counts and carries on (include/raingun_b200.h):
+    a hit point no face of a far-away box is within 1e-8 of -> `assert!(false)` bodies.rs:324; a sphere
+    with an infinite centre -> NaN distance -> `partial_cmp().unwrap()` scene.rs:38.  Oracle and device
+    must agree on the counts and on every pixel."""
+    from raingun_b200.scene import scene_from_dict
+
+    mat = lambda s="Diffuse": {"coloration": {"Color": "#c0c0c0"}, "albedo": 0.5, "surface": s}
+    doc = {"maxRecursionDepth": 4,
+           "lights": [{"Directional": {"direction": [0.2, -1.0, -0.3], "color": "#ffffff", "intensity": 5.0}}],
+           "bodies": [
+               {"Plane": {"origin": [0.0, -2.0, 0.0], "normal": [0.0, -1.0, 0.0], "material": mat({"Reflecting": {"reflectivity": 0.5}})}},
+               {"AABB": {"bounds": [[1.0e9, -1.0e8, -1.0e10 + 0.3], [2.0e9 + 0.7, 1.0e8, -3.3e9 - 0.1]], "material": mat()}},
+               {"Sphere": {"center": [-2.5, 0.0, -5.0], "radius": 1.0, "material": mat({"Refractive": {"index": 1.5, "transparency": 0.9}})}}]}
+    far_box = scene_from_dict(doc)
+    doc["bodies"].append({"Sphere": {"center": [float("inf"), 0.0, -5.0], "radius": 1.0, "material": mat()}})
+    nan_sphere = scene_from_dict(doc)
+    w, h = 224, 126
+    for label, data, want_nan, want_aabb in (("far box", far_box, False, True), ("infinite sphere", nan_sphere, True, True)):
+        ref, ost, _ = oracle.render(data, w, h)
+        assert (ost.err_nan_distance > 0) == want_nan and (ost.err_aabb_normal > 0) == want_aabb
+        for mode in MODES:
+            img, st = _render(data, w, h, mode[1], mode[2])
+            _assert_same(img, ref, st, ost, f"{label}/{mode[0]}")

@@ -56,6 +56,21 @@ def test_native_loader_equals_python_loader_on_synthetic_yaml(cfg, spheres):
     assert native.n_bodies == spheres + 1
 
 
+@pytest.mark.parametrize("flow", [False, True, None], ids=["block", "flow", "mixed"])
+@pytest.mark.parametrize("width", [80, 30, 100000])
+def test_yaml_styles_emitted_by_another_yaml_library(flow, width):
+    """The same scene document written by PyYAML in block style, in flow style (one long line or
+    wrapped at 30 columns, i.e. flow collections continued over many lines) and mixed."""
+    import yaml
+
+    data, spec = make_scene("C5", spheres=60, texture_loader=bundled_texture_loader)
+    doc = make_scene_doc(spec, 60)
+    text = yaml.safe_dump(doc, sort_keys=False, default_flow_style=flow, width=width)
+    assert_same_scene(host.parse_scene(text, bundled_texture_loader), data)
+    text2 = "%YAML 1.1\n--- # scene\n" + yaml.safe_dump(doc, sort_keys=True, default_flow_style=flow, width=width, indent=6) + "...\n"
+    assert_same_scene(host.parse_scene(text2, bundled_texture_loader), data)
+
+
 def test_yaml_forms_the_reference_schema_allows():
     text = """
 # comment line
