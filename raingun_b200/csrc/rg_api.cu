@@ -169,25 +169,40 @@ static double fov_adjustment(double fov_degrees) {
     return std::tan((fov_degrees * (pi / 180.0)) / 2.0);
 }
 
+// RGB8 / RGBA8 texels as uploaded -> the uchar4 rows of a pitch-linear texture.
+// DynamicImage::get_pixel yields Rgba<u8> (material.rs:67); RGB sources get alpha 255.
+__global__ void __launch_bounds__(256) k_tex_expand(const uint8_t *__restrict__ src, uint32_t channels, uint32_t w, uint32_t h,
+                                                    uint8_t *dst, size_t pitch) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    const uint8_t *p = src + ((size_t)y * w + x) * channels;
+    *reinterpret_cast<uchar4 *>(dst + (size_t)y * pitch + (size_t)x * 4) = make_uchar4(p[0], p[1], p[2], channels == 4 ? p[3] : 255);
+}
+
+// Textures are CUDA texture objects (point sampling, unnormalised coordinates: the integer texel is
+// computed exactly as Texture::wrap does, material.rs:70-79) over PITCH-LINEAR memory carved from the
+// scene arena: cudaMallocArray / cudaFreeArray cost 8-100 ms per scene on this driver (measured),
+// the arena costs nothing once it exists, and the RGB -> RGBA expansion runs on the device.
 static int create_textures(rg_scene *sc, const rg_scene_desc *d) {
     std::vector<DTex> host(d->n_textures);
     for (uint32_t i = 0; i < d->n_textures; ++i) {
         const rg_texture_desc &t = d->textures[i];
-        // DynamicImage::get_pixel yields Rgba<u8> (material.rs:67); RGB sources get alpha 255.
-        std::vector<uchar4> rgba((size_t)t.width * t.height);
-        for (size_t p = 0; p < rgba.size(); ++p) {
-            const uint8_t *src = t.pixels + p * t.channels;
-            rgba[p] = make_uchar4(src[0], src[1], src[2], t.channels == 4 ? src[3] : 255);
-        }
-        cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
-        cudaArray_t arr = nullptr;
-        RG_CUDA(cudaMallocArray(&arr, &fmt, t.width, t.height));
-        sc->tex_arrays.push_back(arr);
-        RG_CUDA(cudaMemcpy2DToArray(arr, 0, 0, rgba.data(), (size_t)t.width * 4, (size_t)t.width * 4, t.height,
-                                    cudaMemcpyHostToDevice));
+        const size_t raw_bytes = (size_t)t.width * t.height * t.channels;
+        const size_t pitch = ((size_t)t.width * 4 + 511) & ~(size_t)511;
+        uint8_t *raw = static_cast<uint8_t *>(sc->arena.alloc(raw_bytes));
+        uint8_t *lin = static_cast<uint8_t *>(sc->arena.alloc(pitch * t.height + 512));
+        if (!raw || !lin) return RG_E_NOMEM;
+        lin = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(lin) + 511) & ~(uintptr_t)511);   // textureAlignment
+        RG_CUDA(cudaMemcpyAsync(raw, t.pixels, raw_bytes, cudaMemcpyHostToDevice, sc->stream));
+        k_tex_expand<<<dim3((t.width + 255) / 256, t.height), 256, 0, sc->stream>>>(raw, t.channels, t.width, t.height, lin, pitch);
+        RG_CUDA(cudaGetLastError());
         cudaResourceDesc res{};
-        res.resType = cudaResourceTypeArray;
-        res.res.array.array = arr;
+        res.resType = cudaResourceTypePitch2D;
+        res.res.pitch2D.devPtr = lin;
+        res.res.pitch2D.desc = cudaCreateChannelDesc<uchar4>();
+        res.res.pitch2D.width = t.width;
+        res.res.pitch2D.height = t.height;
+        res.res.pitch2D.pitchInBytes = pitch;
         cudaTextureDesc td{};
         td.addressMode[0] = cudaAddressModeClamp;
         td.addressMode[1] = cudaAddressModeClamp;
@@ -201,6 +216,7 @@ static int create_textures(rg_scene *sc, const rg_scene_desc *d) {
         host[i].w = t.width;
         host[i].h = t.height;
     }
+    if (d->n_textures) RG_CUDA(cudaStreamSynchronize(sc->stream));   // the caller's pixel buffers may go away
     return upload(sc, host.data(), host.size(), &sc->ds.tex);
 }
 
@@ -365,7 +381,6 @@ void rg_scene_destroy(rg_scene *sc) {
     if (!sc) return;
     cudaSetDevice(sc->device);
     for (auto o : sc->tex_objs) cudaDestroyTextureObject(o);
-    for (auto a : sc->tex_arrays) cudaFreeArray(a);
     {
         std::lock_guard<std::mutex> lock(g_park_mutex);
         std::vector<ParkedContext> &parked = g_parked[sc->device];

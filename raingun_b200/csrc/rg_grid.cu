@@ -20,7 +20,7 @@ static int upload_vec(rg_scene *sc, const std::vector<T> &v, const T **out) {
     return RG_OK;
 }
 
-int grid_build(rg_scene *sc, const std::vector<double> &sph, const std::vector<float4> &cull) {
+static int grid_build_host(rg_scene *sc, const std::vector<double> &sph, const std::vector<float4> &cull) {
     GridDev &g = sc->ds.grid;
     g = GridDev{};
     const uint32_t n = sc->ds.n_spheres;
@@ -137,5 +137,225 @@ int grid_build(rg_scene *sc, const std::vector<double> &sph, const std::vector<f
     g.enabled = 1;
     return RG_OK;
 }
+
+// ---- the same structure built ON THE DEVICE ---------------------------------------------------
+// The host loops above cost 1.4 ms for 10,000 spheres and 20 ms for 100,000 (measured on the B200
+// box), i.e. most of a scene upload; the sphere list and the cull records are already in HBM at
+// this point, so binning is four small kernels.  Only the bounding box (one pass over the
+// centres), the resolution and two counters stay on the host.  All binning arithmetic is the host
+// builder's, in FP64 without contraction, and every cell list is sorted by sphere index, so both
+// builders produce the same records bit for bit (RG_GRID_BUILD=host selects the host one; the
+// parity tests compare images and exact-test counts of the two).
+struct GridBuildParams {
+    double lo[3], csz[3], P[3];
+    int dim[3];
+    uint32_t n;
+};
+enum : uint32_t { GB_LOOSE = 0, GB_KEPT = 1, GB_TOTAL = 2 };
+constexpr uint32_t kGbLooseTmp = 1024;
+constexpr uint64_t kGbMaxCellsPerSphere = 512;
+
+// 0 = not binned (non-finite / huge), 1 = loose (spans too many cells), 2 = kept; cell range in a, b
+__device__ __forceinline__ int gb_classify(const GridBuildParams &p, const double4 sp, int a[3], int b[3]) {
+    const double c[3] = {sp.x - p.P[0], sp.y - p.P[1], sp.z - p.P[2]};
+    const double r = fabs(sp.w);
+    const bool ok = isfinite(c[0]) && isfinite(c[1]) && isfinite(c[2]) && isfinite(r) && fabs(c[0]) < 1e6 &&
+                    fabs(c[1]) < 1e6 && fabs(c[2]) < 1e6 && r < 1e6;
+    if (!ok) return 0;
+    uint64_t span = 1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double fa = (c[k] - r - p.lo[k]) / p.csz[k] - 2.0 * kGridInflate;
+        const double fb = (c[k] + r - p.lo[k]) / p.csz[k] + 2.0 * kGridInflate;
+        a[k] = max(0, min(p.dim[k] - 1, (int)floor(fa)));
+        b[k] = max(0, min(p.dim[k] - 1, (int)floor(fb)));
+        span *= (uint64_t)(b[k] - a[k] + 1);
+    }
+    return span > kGbMaxCellsPerSphere ? 1 : 2;
+}
+
+__global__ void __launch_bounds__(256) k_gb_count(const GridBuildParams p, const double4 *__restrict__ sph, uint32_t *count,
+                                                  uint32_t *ctr, uint32_t *loose_tmp) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    int a[3], b[3];
+    const int kind = gb_classify(p, sph[i], a, b);
+    if (kind != 2) {   // loose: tested per ray (non-finite spheres are never culled by their records)
+        const uint32_t pos = atomicAdd(&ctr[GB_LOOSE], 1u);
+        if (pos < kGbLooseTmp) loose_tmp[pos] = i;
+        return;
+    }
+    atomicAdd(&ctr[GB_KEPT], 1u);
+    for (int z = a[2]; z <= b[2]; ++z)
+        for (int y = a[1]; y <= b[1]; ++y)
+            for (int x = a[0]; x <= b[0]; ++x) atomicAdd(&count[((size_t)z * p.dim[1] + y) * p.dim[0] + x], 1u);
+}
+
+// exclusive prefix sum of count[0, n) in place, count[n] = total; one 1024-thread block
+__global__ void __launch_bounds__(1024) k_gb_scan(uint32_t *count, uint32_t n, uint32_t *ctr) {
+    __shared__ uint32_t part[1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (n + 1023u) / 1024u;
+    const uint32_t lo = min(n, t * per), hi = min(n, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; ++i) sum += count[i];
+    part[t] = sum;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024u; off <<= 1) {   // Hillis-Steele inclusive scan of the partials
+        const uint32_t v = t >= off ? part[t - off] : 0u;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = t ? part[t - 1] : 0u;
+    for (uint32_t i = lo; i < hi; ++i) {
+        const uint32_t c = count[i];
+        count[i] = run;
+        run += c;
+    }
+    if (t == 1023u) {
+        count[n] = part[1023];
+        ctr[GB_TOTAL] = part[1023];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gb_fill(const GridBuildParams p, const double4 *__restrict__ sph,
+                                                 const uint32_t *__restrict__ start, uint32_t *cursor, uint32_t *items) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    int a[3], b[3];
+    if (gb_classify(p, sph[i], a, b) != 2) return;
+    for (int z = a[2]; z <= b[2]; ++z)
+        for (int y = a[1]; y <= b[1]; ++y)
+            for (int x = a[0]; x <= b[0]; ++x) {
+                const size_t c = ((size_t)z * p.dim[1] + y) * p.dim[0] + x;
+                items[start[c] + atomicAdd(&cursor[c], 1u)] = i;
+            }
+}
+
+// per cell: sort its list by sphere index (the atomics above fill it in arbitrary order), copy the
+// cull records next to it and write the inline 48-byte record (see grid_build_host)
+__global__ void __launch_bounds__(256) k_gb_finish(uint32_t ncells, const uint32_t *__restrict__ start, uint32_t *items,
+                                                   const float4 *__restrict__ cull4, float4 *items_cull, float4 *recs) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const uint32_t b0 = start[c], b1 = start[c + 1], n = b1 - b0;
+    for (uint32_t i = b0 + 1; i < b1; ++i) {   // insertion sort: lists are short (mean < 1, rarely > 8)
+        const uint32_t v = items[i];
+        uint32_t j = i;
+        while (j > b0 && items[j - 1] > v) { items[j] = items[j - 1]; --j; }
+        items[j] = v;
+    }
+    for (uint32_t i = b0; i < b1; ++i) items_cull[i] = cull4[items[i]];
+    const float kInf = __int_as_float(0x7f800000);
+    recs[3 * (size_t)c] = n > 0 ? items_cull[b0] : make_float4(0.f, 0.f, 0.f, kInf);
+    recs[3 * (size_t)c + 1] = n > 1 ? items_cull[b0 + 1] : make_float4(0.f, 0.f, 0.f, kInf);
+    const uint4 meta = make_uint4(n > 0 ? items[b0] : 0xFFFFFFFFu, n > 1 ? items[b0 + 1] : 0xFFFFFFFFu, n > 2 ? b0 + 2 : 0u,
+                                  n > 2 ? b1 : 0u);
+    *reinterpret_cast<uint4 *>(&recs[3 * (size_t)c + 2]) = meta;
+}
+
+__global__ void k_gb_sort_loose(const uint32_t *tmp, uint32_t n, uint32_t *out) {   // n <= 256: one thread
+    if (blockIdx.x || threadIdx.x) return;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t v = tmp[i];
+        uint32_t j = i;
+        while (j > 0 && out[j - 1] > v) { out[j] = out[j - 1]; --j; }
+        out[j] = v;
+    }
+}
+
+static int grid_build_device(rg_scene *sc, const std::vector<double> &sph) {
+    GridDev &g = sc->ds.grid;
+    g = GridDev{};
+    const uint32_t n = sc->ds.n_spheres;
+    if (n < 8) return RG_OK;
+    // host: bounding box of the binnable spheres and the resolution (same arithmetic as grid_build_host)
+    const double *P = sc->ds.cull_ref;
+    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    bool have = false;
+    size_t binned = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const double c[3] = {sph[4 * (size_t)i] - P[0], sph[4 * (size_t)i + 1] - P[1], sph[4 * (size_t)i + 2] - P[2]};
+        const double r = std::fabs(sph[4 * (size_t)i + 3]);
+        const bool ok = std::isfinite(c[0]) && std::isfinite(c[1]) && std::isfinite(c[2]) && std::isfinite(r) &&
+                        std::fabs(c[0]) < 1e6 && std::fabs(c[1]) < 1e6 && std::fabs(c[2]) < 1e6 && r < 1e6;
+        if (!ok) continue;
+        ++binned;
+        for (int k = 0; k < 3; ++k) {
+            if (!have) { lo[k] = c[k] - r; hi[k] = c[k] + r; }
+            else { lo[k] = std::fmin(lo[k], c[k] - r); hi[k] = std::fmax(hi[k], c[k] + r); }
+        }
+        have = true;
+    }
+    if (binned < 8) return RG_OK;
+    const double kDensity = 4.0;
+    double ext[3], vol = 1.0;
+    for (int k = 0; k < 3; ++k) { ext[k] = std::fmax(hi[k] - lo[k], 1e-9); vol *= ext[k]; }
+    const double cell = std::cbrt(vol / (kDensity * (double)binned));
+    if (!(cell > 0.0) || !std::isfinite(cell)) return RG_OK;
+    GridBuildParams p{};
+    p.n = n;
+    for (int k = 0; k < 3; ++k) {
+        p.dim[k] = (int)std::min(256.0, std::max(1.0, std::ceil(ext[k] / cell)));
+        const double c0 = ext[k] / p.dim[k];
+        lo[k] -= 0.02 * c0;
+        hi[k] += 0.02 * c0;
+        p.lo[k] = lo[k];
+        p.csz[k] = (hi[k] - lo[k]) / p.dim[k];
+        p.P[k] = P[k];
+    }
+    const size_t ncells = (size_t)p.dim[0] * p.dim[1] * p.dim[2];
+
+    uint32_t *start = static_cast<uint32_t *>(sc->arena.alloc((ncells + 1) * sizeof(uint32_t)));
+    uint32_t *cursor = static_cast<uint32_t *>(sc->arena.alloc(ncells * sizeof(uint32_t)));
+    uint32_t *ctr = static_cast<uint32_t *>(sc->arena.alloc(4 * sizeof(uint32_t)));
+    uint32_t *loose_tmp = static_cast<uint32_t *>(sc->arena.alloc(kGbLooseTmp * sizeof(uint32_t)));
+    float4 *recs = static_cast<float4 *>(sc->arena.alloc(ncells * 3 * sizeof(float4)));
+    if (!start || !cursor || !ctr || !loose_tmp || !recs) return RG_E_NOMEM;
+    cudaStream_t st = sc->stream;
+    RG_CUDA(cudaMemsetAsync(start, 0, (ncells + 1) * sizeof(uint32_t), st));
+    RG_CUDA(cudaMemsetAsync(cursor, 0, ncells * sizeof(uint32_t), st));
+    RG_CUDA(cudaMemsetAsync(ctr, 0, 4 * sizeof(uint32_t), st));
+    const unsigned sblocks = (n + 255) / 256;
+    k_gb_count<<<sblocks, 256, 0, st>>>(p, sc->ds.sph, start, ctr, loose_tmp);
+    k_gb_scan<<<1, 1024, 0, st>>>(start, (uint32_t)ncells, ctr);
+    uint32_t h_ctr[4] = {0, 0, 0, 0};
+    RG_CUDA(cudaMemcpyAsync(h_ctr, ctr, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
+    RG_CUDA(cudaStreamSynchronize(st));
+    RG_CUDA(cudaGetLastError());
+    const uint32_t n_loose = h_ctr[GB_LOOSE], n_kept = h_ctr[GB_KEPT], total = h_ctr[GB_TOTAL];
+    if (n_loose > 256 || n_kept < 8) return RG_OK;   // not a scene a uniform grid suits
+    uint32_t *items = static_cast<uint32_t *>(sc->arena.alloc((size_t)std::max<uint32_t>(total, 1) * sizeof(uint32_t)));
+    float4 *items_cull = static_cast<float4 *>(sc->arena.alloc((size_t)std::max<uint32_t>(total, 1) * sizeof(float4)));
+    uint32_t *loose = static_cast<uint32_t *>(sc->arena.alloc((size_t)std::max<uint32_t>(n_loose, 1) * sizeof(uint32_t)));
+    if (!items || !items_cull || !loose) return RG_E_NOMEM;
+    k_gb_fill<<<sblocks, 256, 0, st>>>(p, sc->ds.sph, start, cursor, items);
+    k_gb_finish<<<(unsigned)((ncells + 255) / 256), 256, 0, st>>>((uint32_t)ncells, start, items, sc->ds.cull4, items_cull, recs);
+    if (n_loose) k_gb_sort_loose<<<1, 32, 0, st>>>(loose_tmp, n_loose, loose);
+    RG_CUDA(cudaGetLastError());
+    RG_CUDA(cudaStreamSynchronize(st));
+
+    g.cell_rec = recs;
+    g.cell_start = start;
+    g.cell_items = items;
+    g.cell_cull4 = items_cull;
+    g.loose = loose;
+    g.n_loose = n_loose;
+    for (int k = 0; k < 3; ++k) {
+        g.lo[k] = (float)p.lo[k];
+        g.cell[k] = (float)p.csz[k];
+        g.inv_cell[k] = (float)(1.0 / p.csz[k]);
+        g.dim[k] = p.dim[k];
+    }
+    g.enabled = 1;
+    return RG_OK;
+}
+
+int grid_build(rg_scene *sc, const std::vector<double> &sph, const std::vector<float4> &cull) {
+    static const bool on_host = [] { const char *e = getenv("RG_GRID_BUILD"); return e && std::strcmp(e, "host") == 0; }();
+    return on_host ? grid_build_host(sc, sph, cull) : grid_build_device(sc, sph);
+}
+
 
 }  // namespace rg

@@ -67,7 +67,6 @@ struct rg_scene {
     int device = 0;
     rg::DScene ds{};                    // device pointers inside
     rg::SceneArena arena;               // scene arrays
-    std::vector<cudaArray_t> tex_arrays;
     std::vector<cudaTextureObject_t> tex_objs;
     rg::DCounters *d_counters = nullptr;
     rg::DCounters *h_counters = nullptr;   // pinned

@@ -4,7 +4,8 @@ import numpy as np
 import raingun_b200 as rg
 from raingun_b200.synth import make_scene
 name = sys.argv[1] if len(sys.argv) > 1 else "C4"
-sd, spec = make_scene(name)
+from raingun_b200.examples import bundled_texture_loader
+sd, spec = make_scene(name, texture_loader=bundled_texture_loader)
 w, h = spec.width, spec.height
 with rg.Scene(sd) as sc:
     sc.set_accel(rg.ACCEL_BRUTE)

@@ -3,7 +3,8 @@ sys.path.insert(0, ".")
 import numpy as np, torch
 import raingun_b200 as rg
 from raingun_b200.synth import make_scene
-sd, spec = make_scene(sys.argv[1] if len(sys.argv) > 1 else "C4")
+from raingun_b200.examples import bundled_texture_loader
+sd, spec = make_scene(sys.argv[1] if len(sys.argv) > 1 else "C4", texture_loader=bundled_texture_loader)
 w, h = spec.width, spec.height
 host = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()
 for it in range(6):
