@@ -11,6 +11,7 @@ $CMD > gpurun_out/plain_${TAG}.json 2> gpurun_out/plain_${TAG}.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
     --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launch_${TAG}.log 2>&1
 echo "launch list rc=$?"
+if [ "${LAUNCH_ONLY:-0}" != "0" ]; then exit 0; fi   # refresh the launch list only (kernel captures unchanged)
 $CMD > /dev/null 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_trace_grid -s 18 -c 2 \
     -o gpurun_out/prof_grid_${TAG} -f $CMD > gpurun_out/ncu_grid_${TAG}.log 2>&1
