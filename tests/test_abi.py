@@ -117,3 +117,25 @@ def test_headers_are_plain_c(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr   # rg_device_count() is 0 without a GPU, never negative
+
+
+def test_rust_sys_crate_mirrors_the_header():
+    """integration/raingun-b200-sys cannot be compiled here (no cargo), so at least keep its struct
+    fields and prototypes in step with include/raingun_b200.h: same names, same order."""
+    hdr = open(os.path.join(ROOT, "include", "raingun_b200.h")).read()
+    rs = open(os.path.join(ROOT, "integration", "raingun-b200-sys", "src", "lib.rs")).read()
+
+    def c_fields(name):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        return [re.sub(r"\[.*", "", d.strip().split()[-1].lstrip("*")) for d in body.split(";") if d.strip()]
+
+    def rs_fields(name):
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % name, rs, re.S).group(1)
+        return re.findall(r"pub (\w+):", body)
+
+    for name in ("rg_texture_desc", "rg_scene_desc", "rg_stats"):
+        assert c_fields(name) == rs_fields(name), name
+    c_fns = set(re.findall(r"\b(rg_[a-z_]+)\s*\(", hdr)) - {"rg_rows_cb"}
+    rs_fns = set(re.findall(r"pub fn (rg_[a-z_]+)\(", rs))
+    assert c_fns == rs_fns == set(_native.EXPORTS)
