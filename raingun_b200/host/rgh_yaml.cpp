@@ -73,6 +73,28 @@ void append_utf8(std::string &out, unsigned cp) {
 struct Parser {
     std::vector<Line> lines;
     size_t cur = 0;
+    std::vector<std::pair<std::string, YamlNode>> anchors;   // &name -> node (a later definition shadows an earlier one)
+
+    // "&name rest" -> name, text := rest (left-trimmed).  Anchors name a node for later aliases.
+    bool take_anchor(std::string &text, std::string &name, int line) {
+        if (text.empty() || text[0] != '&') return false;
+        size_t e = 1;
+        while (e < text.size() && !is_space(text[e]) && !std::strchr(",[]{}", text[e])) ++e;
+        name = text.substr(1, e - 1);
+        if (name.empty()) fail(line, "empty anchor name");
+        while (e < text.size() && is_space(text[e])) ++e;
+        text = text.substr(e);
+        return true;
+    }
+    void define_anchor(const std::string &name, const YamlNode &n) { anchors.emplace_back(name, n); }
+    YamlNode alias(const std::string &name, int line) {
+        for (size_t i = anchors.size(); i-- > 0;)
+            if (anchors[i].first == name) {
+                YamlNode n = anchors[i].second;
+                return n;
+            }
+        fail(line, "alias *" + name + " refers to an unknown anchor");
+    }
 
     [[noreturn]] void fail(int line, const std::string &msg, int code = RGH_E_FORMAT) { throw ParseError{code, line, msg}; }
 
@@ -144,7 +166,6 @@ struct Parser {
     }
 
     static void reject_unsupported_start(Parser *p, char c, int line) {
-        if (c == '&' || c == '*') p->fail(line, "anchors and aliases are not supported", RGH_E_UNSUPPORTED);
         if (c == '!') p->fail(line, "tags are not supported", RGH_E_UNSUPPORTED);
         if (c == '|' || c == '>') p->fail(line, "block scalars are not supported", RGH_E_UNSUPPORTED);
         if (c == '%' || c == '@' || c == '`') p->fail(line, "a plain scalar cannot start with this character");
@@ -238,6 +259,23 @@ struct Parser {
             return n;
         }
         if (c == ',' || c == ']' || c == '}') return n;  // empty -> Null
+        if (c == '&') {   // anchored flow node
+            size_t e = pos + 1;
+            while (e < s.size() && !is_space(s[e]) && s[e] != '\n' && !std::strchr(",[]{}", s[e])) ++e;
+            const std::string name = s.substr(pos + 1, e - pos - 1);
+            if (name.empty()) fail(line, "empty anchor name");
+            pos = e;
+            YamlNode v = flow_node(s, pos, line, in_map_value);
+            define_anchor(name, v);
+            return v;
+        }
+        if (c == '*') {
+            size_t e = pos + 1;
+            while (e < s.size() && !is_space(s[e]) && s[e] != '\n' && !std::strchr(",[]{}", s[e])) ++e;
+            const std::string name = s.substr(pos + 1, e - pos - 1);
+            pos = e;
+            return alias(name, line);
+        }
         reject_unsupported_start(this, c, line);
         const size_t start = pos;
         while (pos < s.size() && s[pos] != ',' && s[pos] != ']' && s[pos] != '}' && s[pos] != '\n') ++pos;
@@ -248,6 +286,18 @@ struct Parser {
     // An inline value: the rest of a line after "key:" or "- " (or a whole line).  Flow collections
     // may continue on the following lines until their brackets balance.
     YamlNode inline_value(std::string text, int line) {
+        std::string anchor;
+        if (take_anchor(text, anchor, line)) {
+            if (text.empty()) fail(line, "an anchor must be followed by a node on this line or by an indented block");
+            YamlNode v = inline_value(text, line);
+            define_anchor(anchor, v);
+            return v;
+        }
+        if (text[0] == '*') {
+            std::string name = text.substr(1);
+            rtrim(name);
+            return alias(name, line);
+        }
         const char c = text[0];
         if (c == '[' || c == '{') {
             auto balanced = [](const std::string &s) {
@@ -355,9 +405,19 @@ struct Parser {
             for (const auto &e : n.entries)
                 if (e.first == key) fail(no, "duplicate key `" + key + "`");
             YamlNode value;
+            std::string anchor;
+            if (!rest.empty() && rest[0] == '&') {   // "key: &a" with the node on the following lines
+                std::string probe = rest, name;
+                take_anchor(probe, name, no);
+                if (probe.empty()) {
+                    anchor = name;
+                    rest.clear();
+                }
+            }
             if (rest.empty()) {
                 ++cur;
                 value = nested_or_null(indent, no, true);
+                if (!anchor.empty()) define_anchor(anchor, value);
             } else {
                 value = inline_value(rest, no);
                 ++cur;
@@ -379,9 +439,35 @@ struct Parser {
             const std::string &t = lines[cur].text;
             size_t pos = 1;
             while (pos < t.size() && is_space(t[pos])) ++pos;
+            std::string anchor;
+            if (pos < t.size() && t[pos] == '&') {   // "- &a" / "- &a content": the anchor names the whole item
+                std::string rest = t.substr(pos), name;
+                take_anchor(rest, name, no);
+                anchor = name;
+                pos = t.size() - rest.size();
+            }
             if (pos >= t.size()) {
                 ++cur;
                 n.items.push_back(nested_or_null(indent, no, false));
+                if (!anchor.empty()) define_anchor(anchor, n.items.back());
+            } else if (!anchor.empty()) {
+                const int inner = indent + (int)pos;
+                std::string content = t.substr(pos);
+                lines[cur].indent = inner;
+                lines[cur].text = content;
+                std::string key, rest;
+                if (split_key(content, key, rest, no)) {
+                    // "- &a key: value": an anchor belongs to the NEXT node, which is the key scalar
+                    YamlNode k;
+                    k.kind = YamlNode::Scalar;
+                    k.text = key;
+                    k.line = no;
+                    define_anchor(anchor, k);
+                    n.items.push_back(block(inner));
+                } else {
+                    n.items.push_back(block(inner));
+                    define_anchor(anchor, n.items.back());
+                }
             } else {
                 // "- content": re-read `content` as a block starting at its own column
                 const int inner = indent + (int)pos;

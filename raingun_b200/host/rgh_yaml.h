@@ -1,7 +1,8 @@
 // A small YAML reader for the scene schema (block + flow collections, plain / quoted scalars,
 // comments, one document).  Stands in for yaml-rust 0.3.5 under serde_yaml 0.6.2 (Cargo.lock),
-// which the reference uses at src/main.rs:118.  Anchors, aliases, tags, block scalars (| >) and
-// multi-document streams are outside the subset and are reported as RGH_E_UNSUPPORTED.
+// which the reference uses at src/main.rs:118.  Anchors (&a) and aliases (*a) are resolved by copy;
+// tags, block scalars (| >), merge keys and multi-document streams are outside the subset and are
+// reported as RGH_E_UNSUPPORTED.
 #ifndef RGH_YAML_H
 #define RGH_YAML_H
 

@@ -123,6 +123,50 @@ bodies:
     assert_same_scene(sd, pyscene.parse_scene(text.replace('"#+00aBc"', '"#000abc"').replace("intensity: +2", "intensity: 2")))
 
 
+def test_yaml_anchors_and_aliases():
+    """Hand-written scenes share materials through anchors; serde_yaml resolves them, so must we —
+    in block position, inline, in flow collections, and for whole sequence items."""
+    text = """
+defaultColor: &bg "#102030"
+lights:
+  - &sun
+    Directional:
+      direction: &down [0.0, -1.0, 0.0]
+      color: *bg
+      intensity: &one 1
+  - *sun
+  - Spherical: {position: *down, color: "#ffffff", intensity: *one}
+bodies:
+  - Sphere:
+      center: [0, 0, -3]
+      radius: *one
+      material: &glass
+        coloration: {Color: &white "#ffffff"}
+        albedo: 0.5
+        surface: &refr {Refractive: {index: 1.5, transparency: 0.9}}
+  - Sphere: {center: [2, 0, -4], radius: 0.5, material: *glass}
+  - Plane:
+      origin: [0, -2, 0]
+      normal: *down
+      material:
+        coloration:
+          Color: *white
+        albedo: *one
+        surface: *refr
+  - &ball
+    Sphere: {center: [-2, 0, -4], radius: 0.25, material: {coloration: {Color: *bg}, albedo: 1, surface: &d Diffuse}}
+  - *ball
+  - &kind Sphere: {center: [-3, 0, -4], radius: 0.25, material: {coloration: {Color: *bg}, albedo: 1, surface: *d}}
+"""
+    import yaml
+
+    native = host.parse_scene(text)
+    assert_same_scene(native, pyscene.scene_from_dict(yaml.safe_load(text)))
+    assert native.n_bodies == 6 and native.n_lights == 3
+    assert native.surface_kind.tolist() == [2, 2, 2, 0, 0, 0] and native.body_kind.tolist() == [0, 0, 1, 0, 0, 0]
+    assert np.array_equal(native.body_geom[3], native.body_geom[4])
+
+
 def test_empty_document_is_the_default_scene():
     for text in ("", "---\n", "# nothing\n"):
         sd = host.parse_scene(text)
@@ -146,7 +190,8 @@ def test_empty_document_is_the_default_scene():
     ("bodies:\n  - Sphere: {center: [0,0,0], radius: 1, material: {coloration: {Color: \"#ffffff\"}, albedo: 1, "
      "surface: Reflecting}}\n", host.E_SCHEMA, "Reflecting"),                           # not a unit variant
     ("a: [1, 2\n", host.E_FORMAT, "unterminated flow"),
-    ("a: &x 1\n", host.E_UNSUPPORTED, "anchors"),
+    ("a: *nope\n", host.E_FORMAT, "unknown anchor"),
+    ("a: !!str 1\n", host.E_UNSUPPORTED, "tags"),
     ("a: |\n  text\n", host.E_UNSUPPORTED, "block scalars"),
     ("a: 1\n---\nb: 2\n", host.E_UNSUPPORTED, "multi-document"),
     ("\tfov: 1\n", host.E_FORMAT, "tab"),
