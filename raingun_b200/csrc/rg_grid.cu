@@ -1,6 +1,7 @@
 // rg_grid.cu — host-side construction of the exact-culling grid (rg_grid.cuh) at scene upload.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -8,6 +9,13 @@
 #include "rg_host.h"
 
 namespace rg {
+
+// cells per sphere; measured on the B200 (C4 / C5 ms per frame): 2 -> 26.20 / 266.9, 3 -> 25.71 / 263.9, 4 -> 25.96 / 268.3,
+// 6 -> 26.67 / 282.0, 8 -> 27.35 / 301.3 (RG_GRID_DENSITY overrides, for tuning runs)
+static double grid_density() {
+    static const double d = [] { const char *e = getenv("RG_GRID_DENSITY"); double v = e ? atof(e) : 0.0; return v > 0.0 ? v : 3.0; }();
+    return d;
+}
 
 template <typename T>
 static int upload_vec(rg_scene *sc, const std::vector<T> &v, const T **out) {
@@ -49,7 +57,7 @@ static int grid_build_host(rg_scene *sc, const std::vector<double> &sph, const s
     if (binned.size() < 8) return RG_OK;
 
     // resolution: ~kDensity cells per sphere, cubic cells, at most 256 per axis
-    const double kDensity = 4.0;
+    const double kDensity = grid_density();
     double ext[3], vol = 1.0;
     for (int k = 0; k < 3; ++k) { ext[k] = std::fmax(hi[k] - lo[k], 1e-9); vol *= ext[k]; }
     double cell = std::cbrt(vol / (kDensity * (double)binned.size()));
@@ -108,7 +116,7 @@ static int grid_build_host(rg_scene *sc, const std::vector<double> &sph, const s
 
     // Inline cell records: the first two items of every cell live IN the cell's 48-byte record
     // (their cull records + indices), so a cell visit is one fixed-size fetch and two culls for
-    // every lane; only cells with more than two items (~4 % at the default density) touch the
+    // every lane; only cells with more than two items (a few per cent at the default density) touch the
     // overflow lists above.  Empty slots hold a record that every cullable ray rejects.
     const float kInf = std::numeric_limits<float>::infinity();
     std::vector<float4> recs(ncells * 3);
@@ -289,7 +297,7 @@ static int grid_build_device(rg_scene *sc, const std::vector<double> &sph) {
         have = true;
     }
     if (binned < 8) return RG_OK;
-    const double kDensity = 4.0;
+    const double kDensity = grid_density();
     double ext[3], vol = 1.0;
     for (int k = 0; k < 3; ++k) { ext[k] = std::fmax(hi[k] - lo[k], 1e-9); vol *= ext[k]; }
     const double cell = std::cbrt(vol / (kDensity * (double)binned));

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
             if (go && walking) {
                 if (fresh) {
                     // examine the current cell: its two inline items now, an overflow list (cells with
-                    // more than two items, ~4 %) two items per step below
+                    // more than two items, a few per cent) two items per step below
                     if (cm.x != kNoSphere && !cull_reject(cr, c0)) pend0 = cm.x;
                     if (cm.y != kNoSphere && !cull_reject(cr, c1)) pend1 = cm.y;
                     ok = cm.z;
