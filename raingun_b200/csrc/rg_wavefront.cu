@@ -327,11 +327,12 @@ static int launch_trace(rg_scene *sc, const TraceArgs &ta, bool use_grid, cudaSt
         RG_CUDA(cudaMemsetAsync(tuned.fetch, 0, sizeof(unsigned int), stream));
 #define RG_LAUNCH_RESIDENT(R_, U_, T_, PF_)                                                                                   \
     do {                                                                                                                      \
-        static bool attr_set = false;                                                                                         \
-        if (!attr_set) {                                                                                                      \
+        static uint64_t attr_set = 0; /* per device: the attribute belongs to the device's copy of the function */          \
+        const uint64_t dev_bit = 1ull << (sc->device & 63);                                                                   \
+        if (!(attr_set & dev_bit)) {                                                                                          \
             RG_CUDA(cudaFuncSetAttribute(k_trace_brute_resident<ANY, R_, U_, T_, PF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          kResidentSmemMax));                                                                  \
-            attr_set = true;                                                                                                  \
+            attr_set |= dev_bit;                                                                                              \
         }                                                                                                                     \
         const uint64_t tiles = ((uint64_t)ta.n + 32 * R_ - 1) / (32 * R_);                                                     \
         const unsigned blocks = (unsigned)std::min<uint64_t>((uint64_t)sc->sm_count, (tiles + (T_ / 32) - 1) / (T_ / 32));      \
