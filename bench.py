@@ -64,6 +64,36 @@ def profiled_traffic():
     return None, None
 
 
+def profiled_grid_kernel():
+    """Key ncu metrics of the kernel that dominates the `value` arm (k_trace_grid, nearest + any-hit
+    variants) from the newest committed `--set full` capture; {} when no summary is present."""
+    import glob
+    import re
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_summary.md")), reverse=True):
+        text = open(path).read()
+        out = {}
+        for variant, label in (("0", "nearest"), ("1", "any_hit")):
+            m = re.search(r"### `void k_trace_grid<%s>.*?\n\n(.*?)\n\n" % variant, text, re.S)
+            if not m:
+                continue
+            vals = {}
+            for key, pat in (("ipc", r"IPC \(per SM, active\): ([\d.]+)"), ("issue_slots_busy_pct", r"issue slots busy %: ([\d.]+)"),
+                             ("active_threads_per_warp", r"avg active threads / warp instr: ([\d.]+)"),
+                             ("achieved_occupancy_pct", r"achieved occupancy %: ([\d.]+)"),
+                             ("l1_hit_pct", r"L1/TEX hit rate %: ([\d.]+)"), ("dram_pct_of_peak", r"DRAM throughput % of peak: ([\d.]+)")):
+                mm = re.search(pat, m.group(1))
+                if mm:
+                    vals[key] = round(float(mm.group(1)), 2)
+            sm = re.search(r"top stall reasons.*?: (.*)", m.group(1))
+            if sm:
+                vals["top_stalls"] = sm.group(1).strip()
+            out[label] = vals
+        if out:
+            out["source"] = f"profiles/{os.path.basename(path)}"
+            return out
+    return {}
+
+
 class ClockSampler:
     """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -444,6 +474,12 @@ def main() -> int:
                     "scene_upload_ms_per_step": upload_s[0] / max(1, args.steps) * 1e3,
                     "what": "rg_scene_create (scene H2D) + render + RGBA8 frame D2H into pinned host memory + rg_scene_destroy, per step"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "brute_force": brute,
+            # the kernel that dominates the `value` arm is latency / issue bound, not FP32- or HBM-bound: its
+            # figure of merit is rays/s; the ncu numbers that say so come from the committed capture
+            "value_arm_kernel": {"kernel": "k_trace_grid (exact grid traversal, nearest + any-hit)", "bound": "latency/issue",
+                                 "trace_ms_per_step_sum_of_spans": (last_stats.ms_trace if last_stats else None),
+                                 "device_ms_last_step": (last_stats.ms_device if last_stats else None),
+                                 "rays_per_s": value * 1e6, "ncu": profiled_grid_kernel()},
             "cpu_baseline": cpu_baseline, "frame_checksum": checksum,
         }
         print(json.dumps(line), flush=True)
