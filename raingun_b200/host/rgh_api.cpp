@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -63,16 +65,26 @@ const char *rgh_last_error(void) { return rgh::g_error.c_str(); }
 void *rgh_alloc(size_t n) { return std::malloc(n ? n : 1); }
 void rgh_free(void *p) { std::free(p); }
 
+// Nothing may unwind across the C ABI: allocation failures on absurd (corrupt) dimensions included.
+#define RGH_GUARD(expr)                                                                    \
+    try {                                                                                  \
+        return (expr);                                                                     \
+    } catch (const std::bad_alloc &) {                                                     \
+        return rgh::set_error(RGH_E_FORMAT, "out of memory (corrupt dimensions?)");        \
+    } catch (const std::exception &e) {                                                    \
+        return rgh::set_error(RGH_E_FORMAT, std::string("internal error: ") + e.what());   \
+    }
+
 int rgh_jpeg_decode(const uint8_t *data, size_t len, rgh_image *out) {
     if (!data || !out) return rgh::set_error(RGH_E_INVALID, "rgh_jpeg_decode: null argument");
     std::memset(out, 0, sizeof *out);
-    return rgh::jpeg_decode(data, len, out);
+    RGH_GUARD(rgh::jpeg_decode(data, len, out))
 }
 
 int rgh_png_decode(const uint8_t *data, size_t len, rgh_image *out) {
     if (!data || !out) return rgh::set_error(RGH_E_INVALID, "rgh_png_decode: null argument");
     std::memset(out, 0, sizeof *out);
-    return rgh::png_decode(data, len, out);
+    RGH_GUARD(rgh::png_decode(data, len, out))
 }
 
 int rgh_png_encode(const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t channels, uint8_t **out,
@@ -97,7 +109,7 @@ int rgh_image_open(const char *path, rgh_image *out) {
     if (!jpg && !png) return rgh::set_error(RGH_E_UNSUPPORTED, "Unsupported image format image/" + ext + " (jpg, jpeg and png are built)");
     std::vector<uint8_t> data;
     if (!rgh::read_file(path, data)) return rgh::set_error(RGH_E_IO, std::string(std::strerror(errno)) + " (" + path + ")");
-    return jpg ? rgh::jpeg_decode(data.data(), data.size(), out) : rgh::png_decode(data.data(), data.size(), out);
+    RGH_GUARD(jpg ? rgh::jpeg_decode(data.data(), data.size(), out) : rgh::png_decode(data.data(), data.size(), out))
 }
 
 int rgh_png_save(const char *path, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t channels) {

@@ -55,11 +55,13 @@ struct BitReader {
     uint64_t bits = 0;
     int count = 0;
     int marker = 0;  // a marker met while filling (stops the fill; zeros are fed from then on)
+    bool eof = false;  // the data ended inside an 0xFF sequence: `marker` is a stand-in, not a byte of the file
     void reset(const uint8_t *q) {
         p = q;
         bits = 0;
         count = 0;
         marker = 0;
+        eof = false;
     }
     void fill() {
         while (count <= 56) {
@@ -68,6 +70,7 @@ struct BitReader {
                 b = *p++;
                 if (b == 0xFF) {
                     while (p < end && *p == 0xFF) ++p;  // fill bytes
+                    if (p >= end) eof = true;
                     const uint32_t m = p < end ? *p++ : 0xD9;
                     if (m != 0) {
                         marker = (int)m;
@@ -227,6 +230,7 @@ struct Decoder {
         const int nc = (int)u8();
         if (precision != 8) return fail("unsupported sample precision", RGH_E_UNSUPPORTED);
         if (width == 0 || height == 0) return fail("zero image dimension", RGH_E_UNSUPPORTED);
+        if ((uint64_t)width * (uint64_t)height > (1ull << 28)) return fail("image larger than 2^28 pixels", RGH_E_UNSUPPORTED);
         if (nc != 1 && nc != 3) return fail("unsupported component count", RGH_E_UNSUPPORTED);
         if (pos + (size_t)nc * 3 > end) return fail("short SOF");
         comps.resize((size_t)nc);
@@ -432,10 +436,10 @@ struct Decoder {
         (void)total;
         // continue the marker parse after the entropy-coded data
         br.fill();
-        if (br.marker) {
-            pos = (size_t)(br.p - data) - 2;
-            // fill bytes between the 0xFF and the marker code were skipped: point at an 0xFF
-            while (pos > 0 && data[pos] != 0xFF) --pos;
+        if (br.eof) {
+            pos = len;   // truncated file: never step back to an earlier 0xFF (that would re-read this scan for ever)
+        } else if (br.marker) {
+            pos = (size_t)(br.p - data) - 2;   // the byte before the marker code is an 0xFF (the prefix or a fill byte)
         } else {
             // no marker seen yet: scan forward for one
             size_t q = (size_t)(br.p - data);

@@ -327,7 +327,12 @@ int rgh_scene_parse(const char *yaml, size_t len, const char *texture_root, rgh_
     *out = nullptr;
     rgh::YamlNode doc;
     std::string err;
-    const int rc = rgh::yaml_parse(yaml, len, doc, err);
+    int rc;
+    try {
+        rc = rgh::yaml_parse(yaml, len, doc, err);
+    } catch (const std::exception &e) {
+        return rgh::set_error(RGH_E_FORMAT, std::string("Could not load YAML: ") + e.what());
+    }
     if (rc != RGH_OK) return rgh::set_error(rc, "Could not load YAML: " + err);
     rgh_scene *s = new rgh_scene();
     try {
@@ -335,6 +340,9 @@ int rgh_scene_parse(const char *yaml, size_t len, const char *texture_root, rgh_
     } catch (const rgh::SchemaError &e) {
         rgh_scene_destroy(s);
         return rgh::set_error(e.code, "Could not load YAML: " + e.msg);
+    } catch (const std::exception &e) {   // nothing unwinds across the C ABI
+        rgh_scene_destroy(s);
+        return rgh::set_error(RGH_E_FORMAT, std::string("Could not load YAML: ") + e.what());
     }
     *out = s;
     return RGH_OK;

@@ -74,6 +74,14 @@ struct Parser {
     std::vector<Line> lines;
     size_t cur = 0;
     std::vector<std::pair<std::string, YamlNode>> anchors;   // &name -> node (a later definition shadows an earlier one)
+    int depth = 0;   // nesting of collections being parsed (bounded: the parser recurses)
+    struct Nest {
+        Parser &p;
+        Nest(Parser &q, int line) : p(q) {
+            if (++p.depth > 200) p.fail(line, "collections nested deeper than 200 levels", RGH_E_UNSUPPORTED);
+        }
+        ~Nest() { --p.depth; }
+    };
 
     // "&name rest" -> name, text := rest (left-trimmed).  Anchors name a node for later aliases.
     bool take_anchor(std::string &text, std::string &name, int line) {
@@ -187,6 +195,7 @@ struct Parser {
     }
 
     YamlNode flow_node(const std::string &s, size_t &pos, int line, bool in_map_value) {
+        Nest nest(*this, line);
         skip_ws(s, pos);
         YamlNode n;
         n.line = line;
@@ -371,6 +380,7 @@ struct Parser {
     }
 
     YamlNode block(int indent) {
+        Nest nest(*this, lines[cur].no);
         const Line &l = lines[cur];
         if (is_dash(l.text)) return seq(indent);
         std::string key, rest;

@@ -340,3 +340,50 @@ def test_cli_binary_fails_loudly_without_a_gpu(tmp_path):
         r = subprocess.run([host.CLI_PATH, "--draft", str(scene)], capture_output=True, text=True)
         assert r.returncode == 101 and "Could not upload the scene" in r.stderr
         assert not (tmp_path / "s.png").exists()
+
+
+# ------------------------------------------------------------------------------------ hostile input
+@pytest.mark.timeout(120)
+def test_truncated_and_corrupt_images_fail_cleanly_and_quickly():
+    """The decoders read untrusted files.  A JPEG cut off inside a scan once sent the marker loop back
+    to an earlier 0xFF for ever; corrupt dimensions must not allocate the machine away; nothing may
+    crash or hang (the C++ sources are also fuzzed under ASan/UBSan)."""
+    import struct
+    import zlib
+
+    rng = np.random.default_rng(3)
+    for key in ("texture/textures/tile1/color.jpg", "texture/./textures/land_ocean_ice_cloud_2048.jpg",
+                "texture/./textures/clay-ground-seamless.jpg"):
+        data = _bundle()[key]
+        cuts = sorted(set([3, 20, 200, 700, len(data) // 3, len(data) // 2, len(data) - 2] +
+                          [int(x) for x in rng.integers(2, len(data), 6)]))
+        for cut in cuts:
+            try:
+                img = host.decode_jpeg(data[:cut])       # a prefix may still decode (missing rows are grey)
+                assert img.ndim == 3
+            except host.HostError as e:
+                assert e.code in (host.E_FORMAT, host.E_UNSUPPORTED)
+        # frame header claiming 65535 x 65535
+        i = 2
+        while data[i + 1] not in (0xC0, 0xC1, 0xC2):        # walk the marker segments up to the frame header
+            i += 2 + ((data[i + 2] << 8) | data[i + 3])
+        huge = data[:i + 5] + b"\xff\xff\xff\xff" + data[i + 9:]
+        with pytest.raises(host.HostError):
+            host.decode_jpeg(huge)
+    # PNG: corrupt IDAT, truncated file, absurd dimensions with a valid CRC
+    png = host.encode_png(rng.integers(0, 256, (20, 30, 3), dtype=np.uint8))
+    for bad in (png[:40], png[:-20], png[:60] + b"\x00" * 10 + png[70:]):
+        with pytest.raises(host.HostError):
+            host.decode_png(bad)
+    ihdr = struct.pack(">IIBBBBB", 0x7fffffff, 0x7fffffff, 8, 6, 0, 0, 0)
+    big = png[:8] + struct.pack(">I", 13) + b"IHDR" + ihdr + struct.pack(">I", zlib.crc32(b"IHDR" + ihdr)) + png[33:]
+    with pytest.raises(host.HostError):
+        host.decode_png(big)
+
+
+def test_yaml_nesting_is_bounded():
+    with pytest.raises(host.HostError) as e:
+        host.parse_scene("a: " + "[" * 5000 + "]" * 5000 + "\n")
+    assert e.value.code == host.E_UNSUPPORTED and "nested" in str(e.value)
+    with pytest.raises(host.HostError):
+        host.parse_scene("".join(" " * i + "k:\n" for i in range(400)))
