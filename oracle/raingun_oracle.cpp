@@ -13,11 +13,11 @@
 //   cgmath 0.13.0 (Cargo.lock:97-98)  dot = (x*x' + y*y') + z*z'
 //                                     normalize(v) = v * (1.0 / sqrt(dot(v,v)))
 //                                     cross, +, -, scalar *, 1.0 / Vector3
-// Pinned by the reference's only artefacts for this path: examples/test{1,2,3}.png
-// (tests/test_oracle_golden.py; test2.png is reproduced bit-exactly, test1/test3
-// up to JPEG-decoder differences of the textures: image 0.12.3 / jpeg-decoder
-// 0.1.11 are not vendored, texels come from Pillow — "parity unpinned" at the
-// JPEG decoder only).
+// PINNED by the reference's only artefacts for this path, examples/test{1,2,3}.png: all three
+// renders are reproduced bit for bit (tests/test_oracle_golden.py).  test2.png has no textures
+// and pins the arithmetic; test1.png / test3.png additionally pin the texels, which the hosts
+// decode with raingun_b200/host/rgh_jpeg.cpp — a restatement of jpeg-decoder 0.1.11 (image
+// 0.12.3's JPEG back end, Cargo.lock; not vendored) whose output this oracle only consumes.
 //
 // Every function cites the reference file:line it follows.
 #include <atomic>
