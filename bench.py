@@ -140,6 +140,29 @@ class ClockSampler:
                 "power_w_max": max(power), "samples": len(sm)}
 
 
+def host_description() -> dict:
+    """CPU model, logical cores and the oracle's compiler flags (BASELINE.md section 3 asks for them)."""
+    model = None
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    flags = None
+    try:
+        with open(os.path.join(ROOT, "oracle", "Makefile")) as f:
+            for line in f:
+                if line.startswith("CXXFLAGS"):
+                    flags = line.split("=", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return {"cpu_model": model, "logical_cores": os.cpu_count(), "oracle_cxxflags": flags}
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
 def oracle_sample(data, spec, target_seconds: float, threads=None):
     """Times the CPU oracle (the restated reference algorithm, all host threads, work-stealing
@@ -185,7 +208,8 @@ def run_reference(args, rank):
         "warmup": args.warmup, "ms_per_step": dt / max(1, args.steps) * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.workload, spec, data, {"sample": sample, "parallelism": f"cpu{threads}"}),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": dict({"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                             **host_description()),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ms_per_frame_extrapolated": (rays_per_row * h) / (value * 1e6) * 1e3 if value > 0 else None,
         "note": "reference = CPU restatement of raingun's algorithm (oracle/); cargo/rustc are not in this image",
@@ -454,9 +478,9 @@ def main() -> int:
         t0 = time.perf_counter()
         _, ost, _ = O.render_rows(data, w, h, y0, y1, threads=threads)
         dt = time.perf_counter() - t0
-        cpu_baseline = {"value": ost.rays / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"rows [{y0},{y1}) of {h} ({(y1 - y0) * w} px, {ost.rays} rays) in {dt:.1f} s",
-                        "ms_per_frame_extrapolated": dt * 1e3 * h / max(1, y1 - y0)}
+        cpu_baseline = dict({"value": ost.rays / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"rows [{y0},{y1}) of {h} ({(y1 - y0) * w} px, {ost.rays} rays) in {dt:.1f} s",
+                             "ms_per_frame_extrapolated": dt * 1e3 * h / max(1, y1 - y0)}, **host_description())
 
     if rank == 0:
         line = {
