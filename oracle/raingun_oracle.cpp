@@ -454,14 +454,20 @@ int rgo_render_rows(const rg_scene_desc *desc, uint32_t width, uint32_t height, 
         s.max_depth = max_depth_override;  // main.rs:119-123
     s.default_color = {desc->default_color[0], desc->default_color[1], desc->default_color[2]};
     if (threads < 1) threads = 1;
-    std::atomic<uint32_t> next_row{y0};
+    // rendering.rs:27-35 is a rayon par_iter over PIXELS (adaptive splitting): hand pixels out in
+    // small chunks from a shared counter, so that a short row band still keeps every thread busy
+    const uint64_t total = (uint64_t)(y1 > y0 ? y1 - y0 : 0) * width;
+    const uint64_t kChunk = 64;
+    std::atomic<uint64_t> next_px{0};
     std::vector<Counters> counters((size_t)threads);
     auto worker = [&](int tid) {
         Counters &c = counters[(size_t)tid];
         for (;;) {
-            uint32_t y = next_row.fetch_add(1);
-            if (y >= y1) break;
-            for (uint32_t x = 0; x < width; ++x) {
+            const uint64_t p0 = next_px.fetch_add(kChunk);
+            if (p0 >= total) break;
+            const uint64_t p1 = p0 + kChunk < total ? p0 + kChunk : total;
+            for (uint64_t p = p0; p < p1; ++p) {
+                const uint32_t x = (uint32_t)(p % width), y = y0 + (uint32_t)(p / width);
                 Color col = render_pixel(s, x, y, width, height, c);
                 size_t o = ((size_t)(y - y0) * width + x);
                 rgba_out[4 * o + 0] = f32_as_u8(col.r * 255.0f);  // color.rs:32-37
