@@ -84,16 +84,20 @@ class Scene:
 
     # -- construction, as src/main.rs:117-125 does it
     @classmethod
-    def from_yaml(cls, text: str, device: int = 0, texture_loader=None, max_depth: Optional[int] = None) -> "Scene":
-        from .scene import default_texture_loader
+    def from_yaml(cls, text: str, device: int = 0, texture_loader=None, max_depth: Optional[int] = None,
+                  texture_root: Optional[str] = None) -> "Scene":
+        """The scene is parsed by the native host library (C++ YAML reader + texture decoders,
+        include/raingun_host.h); ``scene.parse_scene`` is the independent Python implementation the
+        tests compare it with."""
+        from . import host
 
-        data = parse_scene(text, texture_loader or default_texture_loader).with_max_depth_limit(max_depth)
-        return cls(data, device)
+        return cls(host.parse_scene(text, texture_loader, texture_root, max_depth), device)
 
     @classmethod
     def from_yaml_file(cls, path: str, device: int = 0, texture_root: Optional[str] = None,
                        max_depth: Optional[int] = None) -> "Scene":
-        return cls(load_scene(path, texture_root).with_max_depth_limit(max_depth), device)
+        with open(path, "r", encoding="utf-8") as f:
+            return cls.from_yaml(f.read(), device, None, max_depth, texture_root)
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:

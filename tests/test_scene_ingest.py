@@ -79,3 +79,28 @@ def test_synthetic_scenes_are_deterministic_and_round_trip_yaml():
     assert c5.coloration_kind.tolist() == [1, 1, 0, 0, 0, 1, 0, 0, 0, 1] and len(c5.textures) == 2
     full = make_scene_doc(SPECS["C3"])
     assert len(full["bodies"]) == 1001 and full["maxRecursionDepth"] == 4 and len(full["lights"]) == 3
+
+
+def test_scene_constructors_use_the_native_loader(monkeypatch, tmp_path):
+    """Scene.from_yaml / from_yaml_file parse with libraingun_host (no PyYAML on the product path);
+    without a GPU the upload then fails loudly with RG_E_CUDA - there is no CPU fallback."""
+    import raingun_b200 as rg
+    from raingun_b200 import host, scene as pyscene
+    from raingun_b200.examples import bundled_texture_loader, example_yaml
+
+    calls = []
+    real = host.parse_scene
+    monkeypatch.setattr(host, "parse_scene", lambda *a, **k: calls.append(1) or real(*a, **k))
+    monkeypatch.setattr(pyscene, "parse_scene", lambda *a, **k: (_ for _ in ()).throw(AssertionError("python loader used")))
+    p = tmp_path / "t2.yml"
+    p.write_text(example_yaml("test2"))
+    if rg.device_count() == 0:
+        for make in (lambda: rg.Scene.from_yaml(example_yaml("test1"), texture_loader=bundled_texture_loader, max_depth=4),
+                     lambda: rg.Scene.from_yaml_file(str(p))):
+            with pytest.raises(rg.RaingunError) as e:
+                make()
+            assert e.value.code == rg._native.E_CUDA
+    else:
+        with rg.Scene.from_yaml_file(str(p)) as sc:
+            assert sc.render_image(64, 48).shape == (48, 64, 4)
+    assert len(calls) >= 1
