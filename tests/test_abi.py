@@ -139,3 +139,33 @@ def test_rust_sys_crate_mirrors_the_header():
     c_fns = set(re.findall(r"\b(rg_[a-z_]+)\s*\(", hdr)) - {"rg_rows_cb"}
     rs_fns = set(re.findall(r"pub fn (rg_[a-z_]+)\(", rs))
     assert c_fns == rs_fns == set(_native.EXPORTS)
+
+
+def test_c_example_host_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    """integration/example_host.c: the whole drop-in from plain C.  Here (no GPU) it must load the
+    scene natively and then stop at the upload with the library's message - never render on the CPU."""
+    import shutil
+    import subprocess
+
+    from raingun_b200 import device_count
+    from raingun_b200.examples import example_yaml
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    pkg = os.path.join(ROOT, "raingun_b200")
+    exe = tmp_path / "example_host"
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "integration", "example_host.c"), "-o", str(exe), "-L", pkg,
+                        "-lraingun_host", "-lraingun_b200", f"-Wl,-rpath,{pkg}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    scene = tmp_path / "test2.yml"
+    scene.write_text(example_yaml("test2"))
+    assert subprocess.run([str(exe)], capture_output=True).returncode == 2
+    r = subprocess.run([str(exe), str(tmp_path / "missing.yml"), str(tmp_path / "o.png")], capture_output=True, text=True)
+    assert r.returncode == 3 and "Could not open input file" in r.stderr
+    r = subprocess.run([str(exe), str(scene), str(tmp_path / "o.png"), "160", "120"], capture_output=True, text=True)
+    if device_count() == 0:
+        assert r.returncode == 4 and "no CUDA device" in r.stderr and not (tmp_path / "o.png").exists()
+    else:
+        assert r.returncode == 0 and (tmp_path / "o.png").exists()
