@@ -241,6 +241,40 @@ __global__ void __launch_bounds__(256) k_gb_fill(const GridBuildParams p, const 
             }
 }
 
+// Ascending in-place sort of a cell's list: insertion sort for the usual handful of items, heap sort
+// beyond that, so that a degenerate scene (tens of thousands of spheres in one cell) costs
+// O(n log n) in its one thread instead of O(n^2).  Host-callable for the unit test in rg_sort_test.
+__host__ __device__ inline void gb_sort_u32(uint32_t *v, uint32_t n) {
+    if (n <= 32u) {
+        for (uint32_t i = 1; i < n; ++i) {
+            const uint32_t x = v[i];
+            uint32_t j = i;
+            while (j > 0 && v[j - 1] > x) { v[j] = v[j - 1]; --j; }
+            v[j] = x;
+        }
+        return;
+    }
+    auto sift = [&](uint32_t root, uint32_t end) {   // max-heap sift-down over v[0, end)
+        const uint32_t x = v[root];
+        for (;;) {
+            uint32_t child = 2u * root + 1u;
+            if (child >= end) break;
+            if (child + 1u < end && v[child + 1u] > v[child]) ++child;
+            if (v[child] <= x) break;
+            v[root] = v[child];
+            root = child;
+        }
+        v[root] = x;
+    };
+    for (uint32_t i = n / 2u; i-- > 0;) sift(i, n);
+    for (uint32_t end = n - 1u; end > 0; --end) {
+        const uint32_t t = v[0];
+        v[0] = v[end];
+        v[end] = t;
+        sift(0u, end);
+    }
+}
+
 // per cell: sort its list by sphere index (the atomics above fill it in arbitrary order), copy the
 // cull records next to it and write the inline 48-byte record (see grid_build_host)
 __global__ void __launch_bounds__(256) k_gb_finish(uint32_t ncells, const uint32_t *__restrict__ start, uint32_t *items,
@@ -248,12 +282,7 @@ __global__ void __launch_bounds__(256) k_gb_finish(uint32_t ncells, const uint32
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
     const uint32_t b0 = start[c], b1 = start[c + 1], n = b1 - b0;
-    for (uint32_t i = b0 + 1; i < b1; ++i) {   // insertion sort: lists are short (mean < 1, rarely > 8)
-        const uint32_t v = items[i];
-        uint32_t j = i;
-        while (j > b0 && items[j - 1] > v) { items[j] = items[j - 1]; --j; }
-        items[j] = v;
-    }
+    gb_sort_u32(items + b0, n);   // lists are short (mean < 1, rarely > 8)
     for (uint32_t i = b0; i < b1; ++i) items_cull[i] = cull4[items[i]];
     const float kInf = __int_as_float(0x7f800000);
     recs[3 * (size_t)c] = n > 0 ? items_cull[b0] : make_float4(0.f, 0.f, 0.f, kInf);
