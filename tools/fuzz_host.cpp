@@ -53,6 +53,20 @@ int main(int argc, char **argv) {
         }
         printf("%s: done\n", name); fflush(stdout);
     }
+    {   // CLI option mapping: random argument vectors from the real vocabulary plus junk
+        static const char *vocab[] = {"-w", "-h", "-o", "--width", "--height", "--output", "--width=12", "--height=", "--4k", "--hd",
+                                      "--draft", "--preview", "--", "-", "-w9", "-h=7", "x.yml", "dir/", "..", "", "4294967296", "-3",
+                                      "+5", "--bogus", "-q", "a/b.c/d", "\xff\xfe", "--output=o.png"};
+        for (int it = 0; it < iters * 4; ++it) {
+            const char *av[12];
+            int ac = 1 + (int)(rnd() % 10);
+            av[0] = "raingun";
+            for (int i = 1; i < ac; ++i) av[i] = vocab[rnd() % (sizeof vocab / sizeof vocab[0])];
+            rgh_cli_options o;
+            if (rgh_cli_parse(ac, av, &o) == 0) { ++ok; volatile size_t n = strlen(o.input) + strlen(o.output); (void)n; } else ++bad;
+        }
+        printf("cli: done\n");
+    }
     printf("ok %ld rejected %ld\n", ok, bad);
     return 0;
 }
