@@ -61,7 +61,14 @@ int rgh_png_decode(const uint8_t *data, size_t len, rgh_image *out);
 int rgh_png_encode(const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t channels,
                    uint8_t **out, size_t *out_len);
 
-/* image::open: chooses the decoder by file extension (jpg/jpeg/png), as image 0.12 does. */
+/* The simple formats among the others image 0.12 opens: BMP (palettes, 16/24/32-bit, bit fields; no
+ * RLE), TGA (true-colour, grey, colour-mapped; raw and RLE), PNM (P1-P6).  L8 / RGB8 / RGBA8. */
+int rgh_bmp_decode(const uint8_t *data, size_t len, rgh_image *out);
+int rgh_tga_decode(const uint8_t *data, size_t len, rgh_image *out);
+int rgh_pnm_decode(const uint8_t *data, size_t len, rgh_image *out);
+
+/* image::open: chooses the decoder by file extension, as image 0.12 does (jpg, jpeg, png, bmp,
+ * tga, pbm, pgm, ppm, pnm here; gif, tiff, webp, ico, hdr are reported as unsupported). */
 int rgh_image_open(const char *path, rgh_image *out);
 int rgh_png_save(const char *path, const uint8_t *pixels, uint32_t width, uint32_t height,
                  uint32_t channels);

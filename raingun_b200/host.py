@@ -24,7 +24,7 @@ ERRORS = {0: "RGH_OK", -1: "RGH_E_INVALID", -2: "RGH_E_IO", -3: "RGH_E_FORMAT", 
           -5: "RGH_E_SCHEMA", -6: "RGH_E_USAGE"}
 
 # every symbol include/raingun_host.h declares
-EXPORTS = ("rgh_jpeg_decode", "rgh_png_decode", "rgh_png_encode", "rgh_image_open", "rgh_png_save", "rgh_free",
+EXPORTS = ("rgh_jpeg_decode", "rgh_png_decode", "rgh_bmp_decode", "rgh_tga_decode", "rgh_pnm_decode", "rgh_png_encode", "rgh_image_open", "rgh_png_save", "rgh_free",
            "rgh_alloc", "rgh_scene_parse", "rgh_scene_load", "rgh_scene_desc", "rgh_scene_limit_depth",
            "rgh_scene_texture_path", "rgh_scene_destroy", "rgh_cli_parse", "rgh_last_error")
 
@@ -64,6 +64,9 @@ def lib() -> ctypes.CDLL:
     L.rgh_jpeg_decode.argtypes = [ctypes.c_char_p, sz, ctypes.POINTER(Image)]
     L.rgh_png_decode.restype = ctypes.c_int
     L.rgh_png_decode.argtypes = [ctypes.c_char_p, sz, ctypes.POINTER(Image)]
+    for name in ("rgh_bmp_decode", "rgh_tga_decode", "rgh_pnm_decode"):
+        getattr(L, name).restype = ctypes.c_int
+        getattr(L, name).argtypes = [ctypes.c_char_p, sz, ctypes.POINTER(Image)]
     L.rgh_png_encode.restype = ctypes.c_int
     L.rgh_png_encode.argtypes = [vp, u32, u32, u32, ctypes.POINTER(vp), ctypes.POINTER(sz)]
     L.rgh_image_open.restype = ctypes.c_int
@@ -121,12 +124,34 @@ def decode_png(data: bytes) -> np.ndarray:
     return _take_image(img)
 
 
+def _decode_with(name: str, data: bytes) -> np.ndarray:
+    img = Image()
+    _check(getattr(lib(), name)(data, len(data), ctypes.byref(img)))
+    return _take_image(img)
+
+
+def decode_bmp(data: bytes) -> np.ndarray:
+    return _decode_with("rgh_bmp_decode", data)
+
+
+def decode_tga(data: bytes) -> np.ndarray:
+    return _decode_with("rgh_tga_decode", data)
+
+
+def decode_pnm(data: bytes) -> np.ndarray:
+    return _decode_with("rgh_pnm_decode", data)
+
+
 def decode_image(data: bytes) -> np.ndarray:
     """Texture bytes -> (H, W, 3|4) uint8 as `DynamicImage::get_pixel` presents them."""
     if data[:2] == b"\xff\xd8":
         a = decode_jpeg(data)
     elif data[:8] == b"\x89PNG\r\n\x1a\n":
         a = decode_png(data)
+    elif data[:2] == b"BM":
+        a = decode_bmp(data)
+    elif data[:1] == b"P" and data[1:2] in b"123456":
+        a = decode_pnm(data)
     else:
         raise HostError(E_UNSUPPORTED, "unsupported image format (jpg and png are built)")
     return np.repeat(a, 3, axis=2) if a.shape[2] == 1 else a

@@ -100,16 +100,40 @@ int rgh_png_encode(const uint8_t *pixels, uint32_t width, uint32_t height, uint3
     return RGH_OK;
 }
 
+int rgh_bmp_decode(const uint8_t *data, size_t len, rgh_image *out) {
+    if (!data || !out) return rgh::set_error(RGH_E_INVALID, "rgh_bmp_decode: null argument");
+    std::memset(out, 0, sizeof *out);
+    RGH_GUARD(rgh::bmp_decode(data, len, out))
+}
+
+int rgh_tga_decode(const uint8_t *data, size_t len, rgh_image *out) {
+    if (!data || !out) return rgh::set_error(RGH_E_INVALID, "rgh_tga_decode: null argument");
+    std::memset(out, 0, sizeof *out);
+    RGH_GUARD(rgh::tga_decode(data, len, out))
+}
+
+int rgh_pnm_decode(const uint8_t *data, size_t len, rgh_image *out) {
+    if (!data || !out) return rgh::set_error(RGH_E_INVALID, "rgh_pnm_decode: null argument");
+    std::memset(out, 0, sizeof *out);
+    RGH_GUARD(rgh::pnm_decode(data, len, out))
+}
+
 /* image 0.12 `open`: the decoder is chosen by the (case-insensitive) extension. */
 int rgh_image_open(const char *path, rgh_image *out) {
     if (!path || !out) return rgh::set_error(RGH_E_INVALID, "rgh_image_open: null argument");
     std::memset(out, 0, sizeof *out);
     const std::string ext = rgh::lower_ext(path);
-    const bool jpg = ext == "jpg" || ext == "jpeg", png = ext == "png";
-    if (!jpg && !png) return rgh::set_error(RGH_E_UNSUPPORTED, "Unsupported image format image/" + ext + " (jpg, jpeg and png are built)");
+    int (*decode)(const uint8_t *, size_t, rgh_image *) = nullptr;
+    if (ext == "jpg" || ext == "jpeg") decode = rgh::jpeg_decode;
+    else if (ext == "png") decode = rgh::png_decode;
+    else if (ext == "bmp") decode = rgh::bmp_decode;
+    else if (ext == "tga") decode = rgh::tga_decode;
+    else if (ext == "pbm" || ext == "pgm" || ext == "ppm" || ext == "pnm") decode = rgh::pnm_decode;
+    if (!decode)
+        return rgh::set_error(RGH_E_UNSUPPORTED, "Unsupported image format image/" + ext + " (jpg, jpeg, png, bmp, tga, pbm, pgm, ppm are built)");
     std::vector<uint8_t> data;
     if (!rgh::read_file(path, data)) return rgh::set_error(RGH_E_IO, std::string(std::strerror(errno)) + " (" + path + ")");
-    RGH_GUARD(jpg ? rgh::jpeg_decode(data.data(), data.size(), out) : rgh::png_decode(data.data(), data.size(), out))
+    RGH_GUARD(decode(data.data(), data.size(), out))
 }
 
 int rgh_png_save(const char *path, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t channels) {

@@ -387,3 +387,63 @@ def test_yaml_nesting_is_bounded():
     assert e.value.code == host.E_UNSUPPORTED and "nested" in str(e.value)
     with pytest.raises(host.HostError):
         host.parse_scene("".join(" " * i + "k:\n" for i in range(400)))
+
+
+def test_bmp_tga_pnm_decoders_against_pillow(tmp_path):
+    """The simple formats `image::open` also accepts (material.rs:42): decode what Pillow writes, in
+    every variant it can write, and compare with Pillow's own reading of the same bytes."""
+    from PIL import Image
+
+    rng = np.random.default_rng(21)
+    base = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    base[10:20, 5:40] = (200, 30, 90)          # runs, so that RLE has something to do
+    rgb = Image.fromarray(base)
+
+    def check(fmt, im, decode, **kw):
+        buf = io.BytesIO()
+        im.save(buf, fmt, **kw)
+        data = buf.getvalue()
+        mine = decode(data)
+        back = Image.open(io.BytesIO(data))
+        want = np.asarray(back.convert({1: "L", 3: "RGB", 4: "RGBA"}[mine.shape[2]]))
+        want = want[..., None] if want.ndim == 2 else want
+        assert mine.shape == want.shape, (fmt, im.mode, kw, mine.shape, want.shape)
+        assert np.array_equal(mine, want), (fmt, im.mode, kw, int(np.abs(mine.astype(int) - want.astype(int)).max()))
+        return data
+
+    for mode in ("RGB", "RGBA", "P", "L", "1"):
+        check("BMP", rgb.convert(mode), host.decode_bmp)
+    for mode in ("RGB", "RGBA", "L", "P"):
+        for rle in (False, True):
+            check("TGA", rgb.convert(mode), host.decode_tga, compression="tga_rle" if rle else None)
+    check("PPM", rgb, host.decode_pnm)
+    check("PPM", rgb.convert("L"), host.decode_pnm)
+    check("PPM", rgb.convert("1"), host.decode_pnm)
+    # ASCII variants and a 16-bit maxval, which Pillow does not write
+    a = base[:4, :5]
+    p3 = ("P3\n# comment\n5 4\n255\n" + " ".join(str(int(v)) for v in a.reshape(-1)) + "\n").encode()
+    assert np.array_equal(host.decode_pnm(p3), a)
+    p2 = ("P2 5 4 1023\n" + "\n".join(" ".join(str(int(v) * 4) for v in row) for row in a[..., 0]) + "\n").encode()
+    assert np.abs(host.decode_pnm(p2)[..., 0].astype(int) - a[..., 0]).max() <= 1
+    p1 = b"P1\n3 2\n1 0 1\n0 1 0\n"
+    assert host.decode_pnm(p1)[..., 0].tolist() == [[0, 255, 0], [255, 0, 255]]
+    # image::open picks the decoder by extension; a texture in one of these formats loads into a scene
+    for ext, fmt in (("bmp", "BMP"), ("tga", "TGA"), ("ppm", "PPM")):
+        path = tmp_path / f"tex.{ext}"
+        rgb.save(path, fmt)
+        assert np.array_equal(host.open_image(str(path)), base)
+    text = ("bodies:\n  - Sphere: {center: [0, 0, -3], radius: 1, material: {coloration: {Texture: {image: tex.bmp, "
+            "x_offset: 0, y_offset: 0}}, albedo: 1, surface: Diffuse}}\n")
+    sd = host.parse_scene(text, texture_root=str(tmp_path))
+    assert np.array_equal(sd.textures[0], base)
+    for ext in ("gif", "webp", "tiff"):
+        (tmp_path / f"t.{ext}").write_bytes(b"xx")
+        with pytest.raises(host.HostError) as e:
+            host.open_image(str(tmp_path / f"t.{ext}"))
+        assert e.value.code == host.E_UNSUPPORTED
+    for decode in (host.decode_bmp, host.decode_tga, host.decode_pnm):
+        for bad in (b"", b"BM", b"P6 4 4 255\nxx", b"\x00" * 17, b"\x00\x00\x02" + b"\x00" * 9 + b"\x10\x00\x10\x00\x18\x00"):
+            try:
+                decode(bad)
+            except host.HostError as e:
+                assert e.code in (host.E_FORMAT, host.E_UNSUPPORTED, host.E_INVALID)

@@ -1,7 +1,7 @@
-// Mutation fuzzer for libraingun_host's parsers (JPEG, PNG, YAML scene), to be built with sanitizers:
+// Mutation fuzzer for libraingun_host's parsers (JPEG, PNG, BMP, TGA, PNM, YAML scene, CLI), to be built with sanitizers:
 //   python tools/fuzz_host_inputs.py /tmp/fz            # writes the seed files from the test bundle
 //   g++ -std=c++17 -O1 -g -fwrapv -fsanitize=address,undefined -Iinclude tools/fuzz_host.cpp \
-//       raingun_b200/host/rgh_{api,jpeg,png,yaml,scene}.cpp -lz -o /tmp/fz/fuzz && (cd /tmp/fz && ./fuzz 4000)
+//       raingun_b200/host/rgh_{api,jpeg,png,simple_formats,yaml,scene}.cpp -lz -o /tmp/fz/fuzz && (cd /tmp/fz && ./fuzz 4000)
 // Truncations, byte flips, 0xFF runs and junk insertions; any sanitizer report or hang is a bug.
 // FUZZ_KEEP_LAST=1 writes each input to last.bin before decoding it (to catch the one that hangs).
 #include <cstdio>
@@ -16,13 +16,15 @@ static uint64_t rnd() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
 static int no_tex(const char *, rgh_image *out, void *) { out->width = out->height = 2; out->channels = 3; out->pixels = (uint8_t *)rgh_alloc(12); memset(out->pixels, 7, 12); return 0; }
 int main(int argc, char **argv) {
     int iters = argc > 1 ? atoi(argv[1]) : 2000;
-    const char *imgs[] = {"a.jpg", "prog.jpg", "base420.jpg", "base422.jpg", "grey.jpg", "rgb.png", "pal.png", "rgba.png", "bit.png"};
+    const char *imgs[] = {"a.jpg", "prog.jpg", "base420.jpg", "base422.jpg", "grey.jpg", "rgb.png", "pal.png", "rgba.png", "bit.png",
+                          "rgb.bmp", "pal.bmp", "rgba.bmp", "rgb.tga", "rle.tga", "pal.tga", "rgb.ppm", "bit.pbm"};
     const char *ymls[] = {"test1.yml", "test2.yml", "test3.yml"};
     long ok = 0, bad = 0;
     for (const char *name : imgs) {
         std::vector<uint8_t> orig = slurp(name);
         if (orig.empty()) { printf("missing %s\n", name); continue; }
-        bool jpg = strstr(name, ".jpg") != nullptr;
+        int (*decode)(const uint8_t *, size_t, rgh_image *) = strstr(name, ".jpg") ? rgh_jpeg_decode : strstr(name, ".png") ? rgh_png_decode
+                                                             : strstr(name, ".bmp") ? rgh_bmp_decode : strstr(name, ".tga") ? rgh_tga_decode : rgh_pnm_decode;
         for (int it = 0; it < iters; ++it) {
             std::vector<uint8_t> d = orig;
             int kind = rnd() % 4;
@@ -32,7 +34,7 @@ int main(int argc, char **argv) {
             else { size_t a = rnd() % d.size(); size_t n = rnd() % 256; d.insert(d.begin() + a, n, (uint8_t)rnd()); }  // insert junk
             if (getenv("FUZZ_KEEP_LAST")) { FILE *f = fopen("last.bin", "wb"); fwrite(d.data(), 1, d.size(), f); fclose(f); }
             rgh_image im; memset(&im, 0, sizeof im);
-            int rc = d.empty() ? -1 : (jpg ? rgh_jpeg_decode(d.data(), d.size(), &im) : rgh_png_decode(d.data(), d.size(), &im));
+            int rc = d.empty() ? -1 : decode(d.data(), d.size(), &im);
             if (rc == 0) { ++ok; volatile uint8_t x = im.pixels[(size_t)im.width * im.height * im.channels - 1]; (void)x; rgh_free(im.pixels); } else ++bad;
         }
         printf("%s: done\n", name); fflush(stdout);

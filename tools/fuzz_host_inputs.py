@@ -21,6 +21,14 @@ im.save(os.path.join(out, "rgb.png"))
 im.convert("P").save(os.path.join(out, "pal.png"))
 im.convert("RGBA").save(os.path.join(out, "rgba.png"))
 im.convert("1").save(os.path.join(out, "bit.png"))
+im.save(os.path.join(out, "rgb.bmp"))
+im.convert("P").save(os.path.join(out, "pal.bmp"))
+im.convert("RGBA").save(os.path.join(out, "rgba.bmp"))
+im.save(os.path.join(out, "rgb.tga"))
+im.save(os.path.join(out, "rle.tga"), compression="tga_rle")
+im.convert("P").save(os.path.join(out, "pal.tga"))
+im.save(os.path.join(out, "rgb.ppm"))
+im.convert("1").save(os.path.join(out, "bit.pbm"))
 for n in ("test1", "test2", "test3"):
     open(os.path.join(out, n + ".yml"), "w").write(example_yaml(n))
 print("seeds written to", out)
