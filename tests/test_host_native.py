@@ -447,3 +447,23 @@ def test_bmp_tga_pnm_decoders_against_pillow(tmp_path):
                 decode(bad)
             except host.HostError as e:
                 assert e.code in (host.E_FORMAT, host.E_UNSUPPORTED, host.E_INVALID)
+
+
+def test_scene_load_from_a_directory_laid_out_like_the_reference(tmp_path):
+    """rgh_scene_load + rgh_image_open by path (what the CLI does): the example scenes and their JPEG
+    textures written to disk load to exactly what the in-memory route produces."""
+    for key, blob in _bundle().items():
+        kind, rel = key.split("/", 1)
+        if kind == "golden":
+            continue
+        path = tmp_path / ("examples/" + rel if kind == "scene" else rel)
+        path.parent.mkdir(parents=True, exist_ok=True)
+        path.write_bytes(blob)
+    for key in ("./textures/clay-ground-seamless.jpg", "textures/tile1/color.jpg"):
+        assert np.array_equal(host.open_image(str(tmp_path / key)), bundled_texture_loader(key))
+    for name in ("test1", "test2", "test3"):
+        from_disk = host.load_scene(str(tmp_path / "examples" / f"{name}.yml"), texture_root=str(tmp_path))
+        assert_same_scene(from_disk, host.parse_scene(example_yaml(name), bundled_texture_loader))
+    with pytest.raises(host.HostError) as e:
+        host.load_scene(str(tmp_path / "examples" / "test1.yml"), texture_root=str(tmp_path / "nowhere"))
+    assert "Could not load texture file ./textures/clay-ground-seamless.jpg" in str(e.value)
