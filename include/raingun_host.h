@@ -66,9 +66,12 @@ int rgh_png_encode(const uint8_t *pixels, uint32_t width, uint32_t height, uint3
 int rgh_bmp_decode(const uint8_t *data, size_t len, rgh_image *out);
 int rgh_tga_decode(const uint8_t *data, size_t len, rgh_image *out);
 int rgh_pnm_decode(const uint8_t *data, size_t len, rgh_image *out);
+/* GIF 87a / 89a: the first frame (what image 0.12 hands to DynamicImage) as RGBA8 on a canvas of the
+ * logical screen size; the transparency index becomes alpha 0. */
+int rgh_gif_decode(const uint8_t *data, size_t len, rgh_image *out);
 
 /* image::open: chooses the decoder by file extension, as image 0.12 does (jpg, jpeg, png, bmp,
- * tga, pbm, pgm, ppm, pnm here; gif, tiff, webp, ico, hdr are reported as unsupported). */
+ * tga, gif, pbm, pgm, ppm, pnm here; tiff, webp, ico, hdr are reported as unsupported). */
 int rgh_image_open(const char *path, rgh_image *out);
 int rgh_png_save(const char *path, const uint8_t *pixels, uint32_t width, uint32_t height,
                  uint32_t channels);

@@ -24,7 +24,8 @@ ERRORS = {0: "RGH_OK", -1: "RGH_E_INVALID", -2: "RGH_E_IO", -3: "RGH_E_FORMAT", 
           -5: "RGH_E_SCHEMA", -6: "RGH_E_USAGE"}
 
 # every symbol include/raingun_host.h declares
-EXPORTS = ("rgh_jpeg_decode", "rgh_png_decode", "rgh_bmp_decode", "rgh_tga_decode", "rgh_pnm_decode", "rgh_png_encode", "rgh_image_open", "rgh_png_save", "rgh_free",
+EXPORTS = ("rgh_jpeg_decode", "rgh_png_decode", "rgh_bmp_decode", "rgh_tga_decode", "rgh_pnm_decode", "rgh_gif_decode",
+           "rgh_png_encode", "rgh_image_open", "rgh_png_save", "rgh_free",
            "rgh_alloc", "rgh_scene_parse", "rgh_scene_load", "rgh_scene_desc", "rgh_scene_limit_depth",
            "rgh_scene_texture_path", "rgh_scene_destroy", "rgh_cli_parse", "rgh_last_error")
 
@@ -64,7 +65,7 @@ def lib() -> ctypes.CDLL:
     L.rgh_jpeg_decode.argtypes = [ctypes.c_char_p, sz, ctypes.POINTER(Image)]
     L.rgh_png_decode.restype = ctypes.c_int
     L.rgh_png_decode.argtypes = [ctypes.c_char_p, sz, ctypes.POINTER(Image)]
-    for name in ("rgh_bmp_decode", "rgh_tga_decode", "rgh_pnm_decode"):
+    for name in ("rgh_bmp_decode", "rgh_tga_decode", "rgh_pnm_decode", "rgh_gif_decode"):
         getattr(L, name).restype = ctypes.c_int
         getattr(L, name).argtypes = [ctypes.c_char_p, sz, ctypes.POINTER(Image)]
     L.rgh_png_encode.restype = ctypes.c_int
@@ -142,6 +143,10 @@ def decode_pnm(data: bytes) -> np.ndarray:
     return _decode_with("rgh_pnm_decode", data)
 
 
+def decode_gif(data: bytes) -> np.ndarray:
+    return _decode_with("rgh_gif_decode", data)
+
+
 def decode_image(data: bytes) -> np.ndarray:
     """Texture bytes -> (H, W, 3|4) uint8 as `DynamicImage::get_pixel` presents them."""
     if data[:2] == b"\xff\xd8":
@@ -150,6 +155,8 @@ def decode_image(data: bytes) -> np.ndarray:
         a = decode_png(data)
     elif data[:2] == b"BM":
         a = decode_bmp(data)
+    elif data[:6] in (b"GIF87a", b"GIF89a"):
+        a = decode_gif(data)
     elif data[:1] == b"P" and data[1:2] in b"123456":
         a = decode_pnm(data)
     else:

@@ -118,6 +118,12 @@ int rgh_pnm_decode(const uint8_t *data, size_t len, rgh_image *out) {
     RGH_GUARD(rgh::pnm_decode(data, len, out))
 }
 
+int rgh_gif_decode(const uint8_t *data, size_t len, rgh_image *out) {
+    if (!data || !out) return rgh::set_error(RGH_E_INVALID, "rgh_gif_decode: null argument");
+    std::memset(out, 0, sizeof *out);
+    RGH_GUARD(rgh::gif_decode(data, len, out))
+}
+
 /* image 0.12 `open`: the decoder is chosen by the (case-insensitive) extension. */
 int rgh_image_open(const char *path, rgh_image *out) {
     if (!path || !out) return rgh::set_error(RGH_E_INVALID, "rgh_image_open: null argument");
@@ -128,9 +134,10 @@ int rgh_image_open(const char *path, rgh_image *out) {
     else if (ext == "png") decode = rgh::png_decode;
     else if (ext == "bmp") decode = rgh::bmp_decode;
     else if (ext == "tga") decode = rgh::tga_decode;
+    else if (ext == "gif") decode = rgh::gif_decode;
     else if (ext == "pbm" || ext == "pgm" || ext == "ppm" || ext == "pnm") decode = rgh::pnm_decode;
     if (!decode)
-        return rgh::set_error(RGH_E_UNSUPPORTED, "Unsupported image format image/" + ext + " (jpg, jpeg, png, bmp, tga, pbm, pgm, ppm are built)");
+        return rgh::set_error(RGH_E_UNSUPPORTED, "Unsupported image format image/" + ext + " (jpg, jpeg, png, bmp, tga, gif, pbm, pgm, ppm are built)");
     std::vector<uint8_t> data;
     if (!rgh::read_file(path, data)) return rgh::set_error(RGH_E_IO, std::string(std::strerror(errno)) + " (" + path + ")");
     RGH_GUARD(decode(data.data(), data.size(), out))

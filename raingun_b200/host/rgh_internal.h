@@ -19,6 +19,7 @@ int png_decode(const uint8_t *data, size_t len, rgh_image *out);
 int bmp_decode(const uint8_t *data, size_t len, rgh_image *out);
 int tga_decode(const uint8_t *data, size_t len, rgh_image *out);
 int pnm_decode(const uint8_t *data, size_t len, rgh_image *out);
+int gif_decode(const uint8_t *data, size_t len, rgh_image *out);
 int png_encode(const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t channels,
                std::vector<uint8_t> &out);
 

@@ -1,4 +1,4 @@
-// BMP, TGA and PNM decoders of the native host library — the simple formats among those
+// BMP, TGA, PNM and GIF decoders of the native host library — the simple formats among those
 // `image::open` accepts in the reference (image 0.12.3 default features: bmp, tga, ppm besides
 // jpeg / png / gif / tiff / webp / ico / hdr; material.rs:42).  Output as the other decoders:
 // RGB8 or RGBA8 (or L8 for grey PNM / TGA), rows top to bottom.
@@ -7,6 +7,8 @@
 //   TGA  types 1/2/3 and their RLE forms 9/10/11; 8-bit grey, 15/16/24/32-bit colour, 8-bit
 //        colour-mapped; either vertical origin
 //   PNM  P2/P3/P5/P6 (grey / RGB, ASCII or binary, maxval <= 65535 scaled to 8 bits) and P1/P4 bitmaps
+//   GIF  87a / 89a, first frame only (what image 0.12 hands to `DynamicImage`), global / local colour
+//        tables, interlace, transparency index -> alpha 0; RGBA8 on a canvas of the logical screen size
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -234,6 +236,129 @@ int pnm_decode(const uint8_t *data, size_t len, rgh_image *out) {
     }
     if (!ok) { rgh_free(out->pixels); out->pixels = nullptr; return set_error(RGH_E_FORMAT, "PNM: truncated or malformed pixel data"); }
     return RGH_OK;
+}
+
+int gif_decode(const uint8_t *data, size_t len, rgh_image *out) {
+    if (len < 13 || (std::memcmp(data, "GIF87a", 6) != 0 && std::memcmp(data, "GIF89a", 6) != 0))
+        return set_error(RGH_E_FORMAT, "GIF: bad signature");
+    Reader r{data, len};
+    r.p = 6;
+    const uint32_t SW = r.le16(), SH = r.le16(), flags = r.u8();
+    r.u8(); r.u8();   // background colour index, pixel aspect ratio
+    const uint8_t *gct = nullptr;
+    uint32_t gct_n = 0;
+    if (flags & 0x80) {
+        gct_n = 2u << (flags & 7);
+        if (r.p + (size_t)gct_n * 3 > len) return set_error(RGH_E_FORMAT, "GIF: truncated colour table");
+        gct = data + r.p;
+        r.p += (size_t)gct_n * 3;
+    }
+    int transparent = -1;
+    for (;;) {
+        const uint32_t tag = r.u8();
+        if (!r.ok || tag == 0x3B) return set_error(RGH_E_FORMAT, "GIF: no image data");
+        if (tag == 0x21) {   // extension: only the graphic control extension matters (transparency)
+            const uint32_t label = r.u8();
+            for (;;) {
+                const uint32_t n = r.u8();
+                if (!r.ok) return set_error(RGH_E_FORMAT, "GIF: truncated extension");
+                if (n == 0) break;
+                if (r.p + n > len) return set_error(RGH_E_FORMAT, "GIF: truncated extension");
+                if (label == 0xF9 && n >= 4 && (data[r.p] & 1)) transparent = data[r.p + 3];
+                r.p += n;
+            }
+            continue;
+        }
+        if (tag != 0x2C) return set_error(RGH_E_FORMAT, "GIF: unknown block");
+        break;
+    }
+    const uint32_t fx = r.le16(), fy = r.le16(), fw = r.le16(), fh = r.le16(), iflags = r.u8();
+    const uint8_t *ct = gct;
+    uint32_t ct_n = gct_n;
+    if (iflags & 0x80) {
+        ct_n = 2u << (iflags & 7);
+        if (r.p + (size_t)ct_n * 3 > len) return set_error(RGH_E_FORMAT, "GIF: truncated colour table");
+        ct = data + r.p;
+        r.p += (size_t)ct_n * 3;
+    }
+    const uint32_t min_code = r.u8();
+    if (!r.ok || min_code < 1 || min_code > 11 || fw == 0 || fh == 0) return set_error(RGH_E_FORMAT, "GIF: bad image descriptor");
+    const uint32_t W = SW ? SW : fw, H = SH ? SH : fh;
+    if (!alloc_image(out, W, H, 4)) return set_error(RGH_E_FORMAT, "GIF: bad dimensions");
+    std::memset(out->pixels, 0, (size_t)W * H * 4);   // transparent canvas
+    // LZW over the concatenated sub-blocks
+    std::vector<uint16_t> prefix(4096);
+    std::vector<uint8_t> suffix(4096), stack(4097);
+    const uint32_t clear = 1u << min_code, eoi = clear + 1;
+    uint32_t avail = clear + 2, size = min_code + 1, mask = (1u << size) - 1, old = 0xFFFFFFFFu, first = 0;
+    for (uint32_t i = 0; i < clear; ++i) { prefix[i] = 0; suffix[i] = (uint8_t)i; }
+    uint64_t bits = 0;
+    uint32_t nbits = 0, block = 0;
+    const bool interlace = (iflags & 0x40) != 0;
+    uint64_t produced = 0;
+    const uint64_t total = (uint64_t)fw * fh;
+    auto put = [&](uint8_t idx) {
+        if (produced >= total) return;
+        const uint32_t x = (uint32_t)(produced % fw);
+        uint32_t y = (uint32_t)(produced / fw);
+        ++produced;
+        if (interlace) {   // rows arrive in four passes: 0,8,16.. / 4,12.. / 2,6.. / 1,3..
+            const uint32_t n1 = (fh + 7) / 8, n2 = (fh + 3) / 8, n3 = (fh + 1) / 4;
+            if (y < n1) y = y * 8;
+            else if (y < n1 + n2) y = (y - n1) * 8 + 4;
+            else if (y < n1 + n2 + n3) y = (y - n1 - n2) * 4 + 2;
+            else y = (y - n1 - n2 - n3) * 2 + 1;
+        }
+        const uint32_t X = fx + x, Y = fy + y;
+        if (X >= W || Y >= H || (int)idx == transparent) return;
+        uint8_t *o = out->pixels + ((size_t)Y * W + X) * 4;
+        if (ct && idx < ct_n) { o[0] = ct[3 * idx]; o[1] = ct[3 * idx + 1]; o[2] = ct[3 * idx + 2]; }
+        o[3] = 255;
+    };
+    bool done = false;
+    while (!done) {
+        if (block == 0) {
+            block = r.u8();
+            if (!r.ok || block == 0) break;
+        }
+        bits |= (uint64_t)r.u8() << nbits;
+        if (!r.ok) break;
+        nbits += 8;
+        --block;
+        while (nbits >= size) {
+            uint32_t code = (uint32_t)bits & mask;
+            bits >>= size;
+            nbits -= size;
+            if (code == clear) { avail = clear + 2; size = min_code + 1; mask = (1u << size) - 1; old = 0xFFFFFFFFu; continue; }
+            if (code == eoi) { done = true; break; }
+            if (old == 0xFFFFFFFFu) {
+                if (code >= clear) { done = true; break; }   // corrupt: the first code must be a literal
+                put((uint8_t)code);
+                old = first = code;
+                continue;
+            }
+            const uint32_t in_code = code;
+            uint32_t sp = 0;
+            if (code >= avail) {
+                if (code > avail) { done = true; break; }     // corrupt stream
+                stack[sp++] = (uint8_t)first;
+                code = old;
+            }
+            while (code >= clear && sp < 4096) { stack[sp++] = suffix[code]; code = prefix[code]; }
+            first = suffix[code];
+            stack[sp++] = (uint8_t)first;
+            if (avail < 4096) {
+                prefix[avail] = (uint16_t)old;
+                suffix[avail] = (uint8_t)first;
+                ++avail;
+                if ((avail & mask) == 0 && avail < 4096) { ++size; mask = (1u << size) - 1; }
+            }
+            old = in_code;
+            while (sp) put(stack[--sp]);
+            if (produced >= total) { done = true; break; }
+        }
+    }
+    return RGH_OK;   // a short stream leaves the remaining pixels transparent, as a streaming decoder would
 }
 
 }  // namespace rgh

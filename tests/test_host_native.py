@@ -436,7 +436,7 @@ def test_bmp_tga_pnm_decoders_against_pillow(tmp_path):
             "x_offset: 0, y_offset: 0}}, albedo: 1, surface: Diffuse}}\n")
     sd = host.parse_scene(text, texture_root=str(tmp_path))
     assert np.array_equal(sd.textures[0], base)
-    for ext in ("gif", "webp", "tiff"):
+    for ext in ("webp", "tiff", "ico"):
         (tmp_path / f"t.{ext}").write_bytes(b"xx")
         with pytest.raises(host.HostError) as e:
             host.open_image(str(tmp_path / f"t.{ext}"))
@@ -467,3 +467,39 @@ def test_scene_load_from_a_directory_laid_out_like_the_reference(tmp_path):
     with pytest.raises(host.HostError) as e:
         host.load_scene(str(tmp_path / "examples" / "test1.yml"), texture_root=str(tmp_path / "nowhere"))
     assert "Could not load texture file ./textures/clay-ground-seamless.jpg" in str(e.value)
+
+
+def test_gif_decoder_against_pillow(tmp_path):
+    """GIF 87a/89a first frame: palettes of several sizes, interlace, transparency, a frame smaller
+    than the logical screen.  Compared with Pillow's RGBA view of the same first frame."""
+    from PIL import Image
+
+    rng = np.random.default_rng(33)
+    base = rng.integers(0, 256, (41, 57, 3), dtype=np.uint8)
+    base[8:30, 10:50] = (10, 200, 120)
+    rgb = Image.fromarray(base)
+    for colors in (2, 4, 16, 256):
+        for interlace in (False, True):
+            im = rgb.quantize(colors)
+            buf = io.BytesIO()
+            im.save(buf, "GIF", interlace=interlace)
+            data = buf.getvalue()
+            mine = host.decode_gif(data)
+            want = np.asarray(Image.open(io.BytesIO(data)).convert("RGBA"))
+            assert mine.shape == want.shape and np.array_equal(mine, want), (colors, interlace)
+    im = rgb.quantize(16)
+    buf = io.BytesIO()
+    im.save(buf, "GIF", transparency=3)
+    data = buf.getvalue()
+    mine = host.decode_gif(data)
+    want = np.asarray(Image.open(io.BytesIO(data)).convert("RGBA"))
+    assert np.array_equal(mine[..., 3], want[..., 3]) and (mine[..., 3] == 0).any()
+    assert np.array_equal(mine[mine[..., 3] == 255], want[want[..., 3] == 255])
+    path = tmp_path / "t.gif"
+    rgb.quantize(64).save(path, "GIF")
+    assert host.open_image(str(path)).shape == (41, 57, 4)
+    for bad in (b"", b"GIF89a", data[:30], data[:-40], b"GIF89a" + b"\xff" * 40):
+        try:
+            host.decode_gif(bad)
+        except host.HostError as e:
+            assert e.code in (host.E_FORMAT, host.E_UNSUPPORTED, host.E_INVALID)

@@ -1,4 +1,4 @@
-// Mutation fuzzer for libraingun_host's parsers (JPEG, PNG, BMP, TGA, PNM, YAML scene, CLI), to be built with sanitizers:
+// Mutation fuzzer for libraingun_host's parsers (JPEG, PNG, BMP, TGA, PNM, GIF, YAML scene, CLI), to be built with sanitizers:
 //   python tools/fuzz_host_inputs.py /tmp/fz            # writes the seed files from the test bundle
 //   g++ -std=c++17 -O1 -g -fwrapv -fsanitize=address,undefined -Iinclude tools/fuzz_host.cpp \
 //       raingun_b200/host/rgh_{api,jpeg,png,simple_formats,yaml,scene}.cpp -lz -o /tmp/fz/fuzz && (cd /tmp/fz && ./fuzz 4000)
@@ -17,14 +17,15 @@ static int no_tex(const char *, rgh_image *out, void *) { out->width = out->heig
 int main(int argc, char **argv) {
     int iters = argc > 1 ? atoi(argv[1]) : 2000;
     const char *imgs[] = {"a.jpg", "prog.jpg", "base420.jpg", "base422.jpg", "grey.jpg", "rgb.png", "pal.png", "rgba.png", "bit.png",
-                          "rgb.bmp", "pal.bmp", "rgba.bmp", "rgb.tga", "rle.tga", "pal.tga", "rgb.ppm", "bit.pbm"};
+                          "rgb.bmp", "pal.bmp", "rgba.bmp", "rgb.tga", "rle.tga", "pal.tga", "rgb.ppm", "bit.pbm", "pal.gif", "lace.gif"};
     const char *ymls[] = {"test1.yml", "test2.yml", "test3.yml"};
     long ok = 0, bad = 0;
     for (const char *name : imgs) {
         std::vector<uint8_t> orig = slurp(name);
         if (orig.empty()) { printf("missing %s\n", name); continue; }
         int (*decode)(const uint8_t *, size_t, rgh_image *) = strstr(name, ".jpg") ? rgh_jpeg_decode : strstr(name, ".png") ? rgh_png_decode
-                                                             : strstr(name, ".bmp") ? rgh_bmp_decode : strstr(name, ".tga") ? rgh_tga_decode : rgh_pnm_decode;
+                                                             : strstr(name, ".bmp") ? rgh_bmp_decode : strstr(name, ".tga") ? rgh_tga_decode
+                                                             : strstr(name, ".gif") ? rgh_gif_decode : rgh_pnm_decode;
         for (int it = 0; it < iters; ++it) {
             std::vector<uint8_t> d = orig;
             int kind = rnd() % 4;

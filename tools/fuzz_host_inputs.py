@@ -29,6 +29,8 @@ im.save(os.path.join(out, "rle.tga"), compression="tga_rle")
 im.convert("P").save(os.path.join(out, "pal.tga"))
 im.save(os.path.join(out, "rgb.ppm"))
 im.convert("1").save(os.path.join(out, "bit.pbm"))
+im.quantize(64).save(os.path.join(out, "pal.gif"))
+im.quantize(16).save(os.path.join(out, "lace.gif"), interlace=True, transparency=2)
 for n in ("test1", "test2", "test3"):
     open(os.path.join(out, n + ".yml"), "w").write(example_yaml(n))
 print("seeds written to", out)
