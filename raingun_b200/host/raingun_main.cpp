@@ -50,19 +50,35 @@ int collect_rows(uint32_t y0, uint32_t rows, uint32_t width, const uint8_t *rgba
 
 }  // namespace
 
+const char kUsage[] =
+    "USAGE:\n    raingun [FLAGS] [OPTIONS] <FILE>\n\nFLAGS:\n"
+    "        --4k         Renders in 4K resolution. Explicit width/height overrides.\n"
+    "        --draft      Renders in 800x600 and lower quality settings.\n"
+    "        --hd         Renders in 1080 (HD) resolution. Explicit width/height overrides.\n"
+    "        --help       Prints help information\n"
+    "        --preview    Streams finished row bands while rendering.\n"
+    "    -V, --version    Prints version information\n\nOPTIONS:\n"
+    "    -h, --height <PIXELS>      Height of output image.\n"
+    "    -o, --output <FILENAME>    Specify filename of the rendered image.\n"
+    "    -w, --width <PIXELS>       Width of output image.\n\nARGS:\n"
+    "    <FILE>    The scene definition file, in YAML format.\n";
+
 int main(int argc, char **argv) {
+    // clap's built-ins (`-h` is taken by --height, so help is long-only): print and exit 0
+    for (int i = 1; i < argc; ++i) {
+        if (!std::strcmp(argv[i], "--")) break;
+        if (!std::strcmp(argv[i], "--help")) {
+            std::printf("raingun 0.1.0 (B200 render path)\n\n%s", kUsage);
+            return 0;
+        }
+        if (!std::strcmp(argv[i], "--version") || !std::strcmp(argv[i], "-V")) {
+            std::printf("raingun 0.1.0\n");
+            return 0;
+        }
+    }
     rgh_cli_options opt;
     if (rgh_cli_parse(argc, argv, &opt) != RGH_OK) {
-        std::fprintf(stderr, "error: %s\n\nUSAGE:\n    raingun [FLAGS] [OPTIONS] <FILE>\n\nFLAGS:\n"
-                             "        --4k         Renders in 4K resolution. Explicit width/height overrides.\n"
-                             "        --draft      Renders in 800x600 and lower quality settings.\n"
-                             "        --hd         Renders in 1080 (HD) resolution. Explicit width/height overrides.\n"
-                             "        --preview    Streams finished row bands while rendering.\n\nOPTIONS:\n"
-                             "    -h, --height <PIXELS>      Height of output image.\n"
-                             "    -o, --output <FILENAME>    Specify filename of the rendered image.\n"
-                             "    -w, --width <PIXELS>       Width of output image.\n\nARGS:\n"
-                             "    <FILE>    The scene definition file, in YAML format.\n",
-                     rgh_last_error());
+        std::fprintf(stderr, "error: %s\n\n%s", rgh_last_error(), kUsage);
         return std::strstr(rgh_last_error(), "Could not guess output filename") ? 2 : 1;
     }
     rgh_scene *hs = nullptr;

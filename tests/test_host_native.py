@@ -336,6 +336,10 @@ def test_cli_binary_fails_loudly_without_a_gpu(tmp_path):
     scene.write_text(example_yaml("test2"))
     r = subprocess.run([host.CLI_PATH], capture_output=True, text=True)
     assert r.returncode == 1 and "USAGE" in r.stderr
+    r = subprocess.run([host.CLI_PATH, "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "USAGE" in r.stdout and "--draft" in r.stdout
+    r = subprocess.run([host.CLI_PATH, "-V"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "raingun 0.1.0"   # the reference's crate version
     if device_count() == 0:
         r = subprocess.run([host.CLI_PATH, "--draft", str(scene)], capture_output=True, text=True)
         assert r.returncode == 101 and "Could not upload the scene" in r.stderr
