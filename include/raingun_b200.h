@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RG_ABI_VERSION 1u
+#define RG_ABI_VERSION 2u
 
 /* Largest scene.max_recursion_depth the device path accepts (the reference's
  * default is 10, scene.rs:26; `--draft` lowers it to 4, src/main.rs:74-75). */
@@ -126,8 +126,14 @@ enum {
     RG_OPT_MAX_DEPTH = 3,    /* like main.rs:119-123: lowers max_recursion_depth  */
     RG_OPT_BATCH_PIXELS = 4, /* pixels per wavefront batch (0 = automatic)         */
     RG_OPT_VERIFY_CULL = 5,  /* debug: count FP32-culled pairs the FP64 test hits  */
-    RG_OPT_OVERLAP = 6       /* shadow side of a level concurrent with the next level's path side:
+    RG_OPT_OVERLAP = 6,      /* shadow side of a level concurrent with the next level's path side:
                                 0 = automatic (on with the grid tracer), 1 = off, 2 = on */
+    RG_OPT_HOST_FREE = 7,    /* the level loop without host involvement (device-sized launches, one
+                                synchronisation per frame; render_image is one call, rendering.rs:24-38):
+                                0 = automatic (on), 1 = off (host reads every level's size), 2 = on */
+    RG_OPT_GRAPH = 8,        /* replay the host-free frame as one CUDA graph: 0 = automatic, 1 = off, 2 = on */
+    RG_OPT_TRACE_STATS = 9   /* 1 = the grid tracer counts cells / fetches / cull tests / lane use
+                                (rg_stats.grid_*); an instrumented kernel, slower; results unchanged */
 };
 
 /* Counters and timings of one render call.  A "ray" is one `Scene::trace`
@@ -151,6 +157,15 @@ typedef struct rg_stats {
     uint32_t batches;              /* wavefront batches                              */
     uint32_t max_level;            /* deepest level that traced a ray                */
     uint32_t accel_used;           /* RG_ACCEL_BRUTE | RG_ACCEL_GRID                 */
+    uint32_t host_free;            /* 1 = the frame ran without host synchronisation (RG_OPT_HOST_FREE) */
+    uint32_t graph_replays;        /* batches replayed from a captured CUDA graph    */
+    /* RG_OPT_TRACE_STATS (grid tracer only; zero otherwise) */
+    uint64_t grid_cells;           /* grid cells visited by all rays                 */
+    uint64_t grid_fetches;         /* cell records fetched (occupied cells)          */
+    uint64_t grid_culls;           /* FP32 cull tests                                */
+    uint64_t grid_refills;         /* warp refills from the ray counter              */
+    uint64_t grid_lane_steps;      /* lanes doing scan work, summed over scan iterations */
+    uint64_t grid_lane_slots;      /* 32 x scan iterations (the denominator)         */
 } rg_stats;
 
 typedef struct rg_scene rg_scene;

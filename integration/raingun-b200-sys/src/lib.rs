@@ -4,7 +4,7 @@
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const RG_ABI_VERSION: u32 = 1;
+pub const RG_ABI_VERSION: u32 = 2;
 pub const RG_MAX_DEPTH: u32 = 64;
 pub const RG_MAX_LIGHTS: u32 = 32;
 pub const RG_IPC_HANDLE_BYTES: usize = 64;
@@ -37,6 +37,9 @@ pub const RG_OPT_MAX_DEPTH: i32 = 3; // src/main.rs:119-123
 pub const RG_OPT_BATCH_PIXELS: i32 = 4;
 pub const RG_OPT_VERIFY_CULL: i32 = 5;
 pub const RG_OPT_OVERLAP: i32 = 6;
+pub const RG_OPT_HOST_FREE: i32 = 7;
+pub const RG_OPT_GRAPH: i32 = 8;
+pub const RG_OPT_TRACE_STATS: i32 = 9;
 
 #[repr(C)]
 pub struct rg_texture_desc {
@@ -92,6 +95,14 @@ pub struct rg_stats {
     pub batches: u32,
     pub max_level: u32,
     pub accel_used: u32,
+    pub host_free: u32,
+    pub graph_replays: u32,
+    pub grid_cells: u64,
+    pub grid_fetches: u64,
+    pub grid_culls: u64,
+    pub grid_refills: u64,
+    pub grid_lane_steps: u64,
+    pub grid_lane_slots: u64,
 }
 
 pub enum rg_scene {}

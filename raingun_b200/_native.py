@@ -22,6 +22,7 @@ E_INVALID, E_PORTRAIT, E_TOO_LARGE, E_DEPTH, E_CUDA, E_NOMEM, E_CANCELLED, E_LIG
 PIPELINE_WAVEFRONT, PIPELINE_MEGAKERNEL = 0, 1
 ACCEL_AUTO, ACCEL_BRUTE, ACCEL_GRID = 0, 1, 2
 OPT_PIPELINE, OPT_ACCEL, OPT_MAX_DEPTH, OPT_BATCH_PIXELS, OPT_VERIFY_CULL, OPT_OVERLAP = 1, 2, 3, 4, 5, 6
+OPT_HOST_FREE, OPT_GRAPH, OPT_TRACE_STATS = 7, 8, 9
 
 ROWS_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                            ctypes.POINTER(ctypes.c_uint8), ctypes.c_void_p)

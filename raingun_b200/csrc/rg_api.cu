@@ -74,6 +74,13 @@ void WavefrontScratch::release() {
     rb = nullptr;
 }
 
+void GraphCache::release() {
+    for (auto &e : entries)
+        if (e.exec) cudaGraphExecDestroy(e.exec);
+    entries.clear();
+    seen.clear();
+}
+
 // Scratch arenas outlive a scene: destroying a scene parks its (possibly multi-GB) wavefront
 // buffers here and the next scene created on the same device adopts them, so a host that
 // re-uploads the scene every frame does not pay cudaMalloc/cudaFree for them each time.
@@ -380,6 +387,7 @@ int rg_device_count(void) {
 void rg_scene_destroy(rg_scene *sc) {
     if (!sc) return;
     cudaSetDevice(sc->device);
+    sc->graphs.release();
     for (auto o : sc->tex_objs) cudaDestroyTextureObject(o);
     {
         std::lock_guard<std::mutex> lock(g_park_mutex);
@@ -520,6 +528,17 @@ int rg_scene_set_option(rg_scene *sc, int32_t key, int64_t value) {
         case RG_OPT_OVERLAP:
             if (value < 0 || value > 2) break;
             sc->overlap = (int)value;
+            return RG_OK;
+        case RG_OPT_HOST_FREE:
+            if (value < 0 || value > 2) break;
+            sc->host_free = (int)value;
+            return RG_OK;
+        case RG_OPT_GRAPH:
+            if (value < 0 || value > 2) break;
+            sc->graph = (int)value;
+            return RG_OK;
+        case RG_OPT_TRACE_STATS:
+            sc->trace_stats = value != 0;
             return RG_OK;
         default: break;
     }
@@ -696,6 +715,14 @@ static void accumulate(rg_stats *total, const rg_stats &s) {
     total->ms_trace += s.ms_trace;
     total->gpu_launches += s.gpu_launches;
     total->batches += s.batches;
+    total->graph_replays += s.graph_replays;
+    total->host_free = s.host_free;
+    total->grid_cells += s.grid_cells;
+    total->grid_fetches += s.grid_fetches;
+    total->grid_culls += s.grid_culls;
+    total->grid_refills += s.grid_refills;
+    total->grid_lane_steps += s.grid_lane_steps;
+    total->grid_lane_slots += s.grid_lane_slots;
     if (s.max_level > total->max_level) total->max_level = s.max_level;
     total->accel_used = s.accel_used;
 }

@@ -78,13 +78,16 @@ __device__ __forceinline__ void exact_sphere(const DScene &s, const Ray &ray, ui
     }
 }
 
-template <bool ANY>
+// STATS = true: the instrumented build of the same kernel (RG_OPT_TRACE_STATS) that counts cells visited,
+// records fetched, cull tests, refills and lane use into DCounters::grid_*; results are unchanged.
+template <bool ANY, bool STATS = false>
 __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(const DScene s, const TraceArgs a) {
     const GridDev &g = s.grid;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
-    const uint32_t n_rays = a.n_dev ? *a.n_dev : a.n;
+    const uint32_t n_rays = ray_count(a);
     unsigned n_exact = 0, nan_count = 0;
+    unsigned long long st_cells = 0, st_fetch = 0, st_culls = 0, st_refills = 0, st_lane_steps = 0, st_lane_slots = 0;
 
     // ---- per-lane ray state
     bool active = false;        // this lane owns an unfinished ray
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
             if (lane == 0) base = atomicAdd(a.fetch, (unsigned)__popc(idle));
             base = __shfl_sync(0xffffffffu, base, 0);
             exhausted = base + (uint32_t)__popc(idle) >= n_rays;
+            if (STATS && lane == 0) ++st_refills;
             const uint32_t ri = base + __popc(idle & lanemask_lt);
             if (!active && ri < n_rays) {
                 // ---- set a new ray up: non-sphere bodies, loose spheres, clip to the grid
@@ -271,8 +275,13 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
 #pragma unroll 1
         for (int burst = 0; burst < a.g_burst; ++burst) {
             const bool go = active && pend0 == kNoSphere && pend1 == kNoSphere;
+            if (STATS) {
+                st_lane_steps += (go && walking) ? 1u : 0u;
+                if (lane == 0) st_lane_slots += 32u;
+            }
             if (go && walking) {
                 if (fresh) {
+                    if (STATS) { ++st_cells; st_fetch += (cm.x != kNoSphere) ? 1u : 0u; st_culls += (cm.x != kNoSphere) + (cm.y != kNoSphere); }
                     // examine the current cell: its two inline items now, an overflow list (cells with
                     // more than two items, a few per cent) two items per step below
                     if (cm.x != kNoSphere && !cull_reject(cr, c0)) pend0 = cm.x;
@@ -281,6 +290,7 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
                     oe = cm.w;
                     fresh = false;
                 } else if (ok < oe) {
+                    if (STATS) st_culls += (ok + 1 < oe) ? 2u : 1u;
                     if (!cull_reject(cr, g.cell_cull4[ok])) pend0 = g.cell_items[ok];
                     if (ok + 1 < oe && !cull_reject(cr, g.cell_cull4[ok + 1])) pend1 = g.cell_items[ok + 1];
                     ok += 2;
@@ -347,6 +357,23 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
     if (lane == 0) {
         if (ne) atomicAdd(&a.ctr->exact_tests, ne);
         if (nan_count) atomicAdd(&a.ctr->err_nan, (unsigned long long)nan_count);
+    }
+    if (STATS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            st_cells += __shfl_xor_sync(0xffffffffu, st_cells, o);
+            st_fetch += __shfl_xor_sync(0xffffffffu, st_fetch, o);
+            st_culls += __shfl_xor_sync(0xffffffffu, st_culls, o);
+            st_lane_steps += __shfl_xor_sync(0xffffffffu, st_lane_steps, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&a.ctr->grid_cells, st_cells);
+            atomicAdd(&a.ctr->grid_fetches, st_fetch);
+            atomicAdd(&a.ctr->grid_culls, st_culls);
+            atomicAdd(&a.ctr->grid_refills, st_refills);
+            atomicAdd(&a.ctr->grid_lane_steps, st_lane_steps);
+            atomicAdd(&a.ctr->grid_lane_slots, st_lane_slots);
+        }
     }
 }
 

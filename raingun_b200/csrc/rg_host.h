@@ -61,6 +61,22 @@ struct WavefrontScratch {
     void release();
 };
 
+// Captured host-free frames (rg_wavefront.cu): the launch sequence of a batch depends only on its
+// key (batch geometry, output pointers, options, scratch addresses), so it is captured once into a
+// CUDA graph and replayed; a key must be seen twice before it is worth an instantiation.
+struct GraphEntry {
+    std::vector<uint64_t> key;
+    cudaGraphExec_t exec = nullptr;
+    uint32_t launches = 0;
+    uint64_t last_use = 0;
+};
+struct GraphCache {
+    std::vector<GraphEntry> entries;
+    std::vector<std::vector<uint64_t>> seen;
+    uint64_t tick = 0;
+    void release();
+};
+
 }  // namespace rg
 
 struct rg_scene {
@@ -77,6 +93,7 @@ struct rg_scene {
     uint8_t *h_frame = nullptr;            // pinned staging
     size_t h_frame_cap = 0;
     rg::WavefrontScratch wf;
+    rg::GraphCache graphs;                 // dies with the scene (kernel parameters hold scene pointers by value)
     // options
     int pipeline = RG_PIPELINE_WAVEFRONT;
     int accel = RG_ACCEL_AUTO;
@@ -84,6 +101,10 @@ struct rg_scene {
     uint64_t batch_pixels = 0;
     int verify_cull = 0;
     int overlap = 0;                       // RG_OPT_OVERLAP: 0 auto (on with the grid tracer), 1 off, 2 on
+    int host_free = 0;                     // RG_OPT_HOST_FREE: 0 auto (on), 1 off (host-sized loop), 2 on
+    int graph = 0;                         // RG_OPT_GRAPH: 0 auto, 1 off, 2 on
+    bool trace_stats = false;              // RG_OPT_TRACE_STATS
+    bool host_free_overflowed = false;     // a level once outgrew the default queue capacity: stay with the host-sized loop
     bool scatter_out = false;              // this call stores rows at their place in a full frame (rg_render_rowlist_scatter)
     // derived
     uint32_t n_bodies = 0;

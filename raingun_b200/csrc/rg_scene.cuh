@@ -81,6 +81,15 @@ struct DScene {
     DLight lights[RG_MAX_LIGHTS];
 };
 
+// Per recursion level, for the host-free wavefront loop (rg_wavefront.cu): every launch of a
+// level reads its size from here instead of from the host.  Zeroed at the start of a batch.
+struct DLevelCtr {
+    unsigned int n;                    // path rays of this level (written by k_generate / the level above's k_shade)
+    unsigned int n_lit;                // hits of this level that need shadow rays
+    unsigned int fetch;                // persistent nearest-hit trace of this level: next unclaimed ray
+    unsigned int fetch_shadow;         // ... of this level's shadow trace
+};
+
 // Device-side counters of one render call (zeroed by the host before the call).
 struct DCounters {
     unsigned long long rays[4];        // primary, shadow, reflection, transmission (megakernel only)
@@ -91,6 +100,16 @@ struct DCounters {
     unsigned int q_lit;                // wavefront: hits that need shadow rays
     unsigned int fetch;                // persistent trace kernels: next unclaimed ray of the queue
     unsigned int fetch_shadow;         // ... of the shadow queue (the two kinds of trace run concurrently)
+    // ---- host-free loop
+    unsigned int overflow;             // a level outgrew its queue capacity: the frame is void, the host re-renders
+    unsigned int max_level;            // deepest level that held a ray
+    unsigned long long grid_cells;     // RG_OPT_TRACE_STATS: cells visited / records fetched / cull tests / refills
+    unsigned long long grid_fetches;
+    unsigned long long grid_culls;
+    unsigned long long grid_refills;
+    unsigned long long grid_lane_steps;   // active lanes summed over scan iterations, and the iterations x 32
+    unsigned long long grid_lane_slots;
+    DLevelCtr lvl[RG_MAX_DEPTH + 2];
 };
 
 }  // namespace rg

@@ -42,11 +42,21 @@ struct TraceArgs {
     uint8_t *out_lit;        // ANY: 1 = in light
     DCounters *ctr;
     unsigned int *fetch;     // persistent kernels: the ray counter of THIS launch (ctr->fetch / ctr->fetch_shadow)
-    const unsigned int *n_dev;   // persistent kernels: if set, the ray count is read from device memory (a launch
-                                 // issued before the host knows it; `n` is then only an upper bound)
+    const unsigned int *n_dev;   // if set, the ray count is *n_dev * n_mul, read from device memory (a launch issued
+                                 // before the host knows it); `n` is then the capacity of the queue (an upper bound)
+    uint32_t n_mul;              // 0 means 1; shadow queues: lights per lit hit
+    const unsigned int *void_flag;   // if set and non-zero, the frame is void (a queue overflowed): trace nothing
     int verify;              // RG_OPT_VERIFY_CULL
     int g_refill, g_quorum, g_burst;   // persistent grid kernel tuning (rg_grid.cuh)
 };
+
+// Number of rays this launch has to trace (see TraceArgs::n_dev).
+__device__ __forceinline__ uint32_t ray_count(const TraceArgs &a) {
+    if (!a.n_dev) return a.n;
+    if (a.void_flag && *a.void_flag) return 0u;
+    const unsigned long long v = (unsigned long long)*a.n_dev * (a.n_mul ? a.n_mul : 1u);
+    return v < a.n ? (uint32_t)v : a.n;
+}
 
 // Path queues are dense (seg_len = 0).  Shadow queues hold one segment per light so that
 // neighbouring lanes trace neighbouring hits towards the SAME light (coherent directions).
@@ -168,6 +178,8 @@ k_trace_brute(const DScene s, const TraceArgs a) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t block_base = blockIdx.x * (uint32_t)(R * kTraceThreads);
+    const uint32_t n_rays = ray_count(a);
+    if (block_base >= n_rays) return;   // device-sized launches cover the queue's capacity: surplus blocks leave at once
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const uint32_t nsph = s.n_spheres;
     const uint32_t nchunks = (nsph + kChunkSpheres - 1) / kChunkSpheres;
@@ -197,7 +209,7 @@ k_trace_brute(const DScene s, const TraceArgs a) {
     for (int r = 0; r < R; ++r) {
         const uint32_t slot = r * kTraceThreads + tid;
         const uint32_t i = block_base + slot;
-        const bool active = i < a.n;
+        const bool active = i < n_rays;
         Ray ray;
         ray.o = d3(0, 0, 0);
         ray.d = d3(0, 0, 0);
@@ -290,7 +302,7 @@ k_trace_brute(const DScene s, const TraceArgs a) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const uint32_t slot = r * kTraceThreads + tid;
-                    const bool live = (block_base + slot < a.n) && sph < nsph;
+                    const bool live = (block_base + slot < n_rays) && sph < nsph;
                     const bool rej = cull_reject_half(cr[r], A, B, (j0 + u) & 1);
                     const bool pass = live && !rej;
                     if (a.verify && live && rej) {   // debug: a culled pair must miss exactly
@@ -352,7 +364,7 @@ k_trace_brute(const DScene s, const TraceArgs a) {
     for (int r = 0; r < R; ++r) {
         const uint32_t slot = r * kTraceThreads + tid;
         const uint32_t i = block_base + slot;
-        if (i < a.n) {
+        if (i < n_rays) {
             const uint32_t pi = phys_index(a, i);
             if (ANY) a.out_lit[pi] = best_b[slot] ? 0 : 1;
             else { a.out_t[pi] = best_t[slot]; a.out_body[pi] = best_b[slot]; }
@@ -407,7 +419,8 @@ k_trace_brute_resident(const DScene s, const TraceArgs a, const uint32_t n_recor
 
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const uint32_t nsph = s.n_spheres;
-    const uint32_t n_rays = a.n;
+    const uint32_t n_rays = ray_count(a);
+    if (n_rays == 0) return;   // an empty level of a device-sized frame: do not even load the records
     unsigned long long n_exact = 0;
     unsigned nan_count = 0, unsound = 0;
 

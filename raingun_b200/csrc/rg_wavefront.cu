@@ -37,16 +37,33 @@ struct LevelBuffers {
     float2 *s_ab;
     float4 *lit_bc;
     uint32_t *lit_node;
-    uint32_t n;
+    uint32_t n;            // rays of this level — or, with n_dev, the capacity of its queue
     uint32_t shadow_sl, shadow_sj;   // shadow ray of (lit hit j, light l) lives at l * shadow_sl + j * shadow_sj
     uint32_t can_spawn;    // depth + 1 < max_recursion_depth
+    // host-free loop: sizes live on the device
+    const unsigned int *n_dev;       // the level's ray count (nullptr: n is exact)
+    unsigned int *q_next, *q_lit;    // counters k_shade appends to: children (= next level's n), lit hits
+    uint32_t cap_next;               // capacity of the next level's queue
+    unsigned int *void_flag;         // set when a queue overflows; once set, every later launch does nothing
+    uint32_t level;                  // recursion depth of this level
+    uint32_t count_on_device;        // shadow rays / deepest level are counted in DCounters (host-free loop)
 };
+
+// Size of a level as its kernels see it (host-sized, or read from the device and clamped to the capacity).
+__device__ __forceinline__ uint32_t level_size(uint32_t n, const unsigned int *n_dev, const unsigned int *void_flag) {
+    if (!n_dev) return n;
+    if (void_flag && *void_flag) return 0u;
+    const uint32_t v = *n_dev;
+    return v < n ? v : n;
+}
 
 // rendering.rs:71-72 + ray.rs:37-54: the level-0 queue, one ray per pixel of rows [y0, y1)
 // `rows` (optional) maps the k-th row of the batch to an image row, for row-tile sharding.
 __global__ void __launch_bounds__(256) k_generate(const DScene s, RayQueue q, uint32_t width, uint32_t height,
-                                                  uint32_t y0, uint32_t npix, const uint32_t *__restrict__ rows) {
+                                                  uint32_t y0, uint32_t npix, const uint32_t *__restrict__ rows,
+                                                  unsigned int *n_level0) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && n_level0) *n_level0 = npix;
     if (i >= npix) return;
     const uint32_t k = y0 + i / width, x = i % width;
     const uint32_t y = rows ? rows[k] : k;
@@ -54,9 +71,16 @@ __global__ void __launch_bounds__(256) k_generate(const DScene s, RayQueue q, ui
 }
 
 __global__ void __launch_bounds__(256) k_shade(const DScene s, const LevelBuffers lb, DCounters *ctr) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
-    const bool active = i < lb.n;
+    const uint32_t n_level = level_size(lb.n, lb.n_dev, lb.void_flag);
+    if (lb.count_on_device && blockIdx.x == 0 && threadIdx.x == 0 && n_level) atomicMax(&ctr->max_level, lb.level);
+    __shared__ uint32_t sh_cnt[3];     // lit, reflection, transmission entries of this block
+    __shared__ uint32_t sh_base[2];    // block base in the lit / next-level queues
+    __shared__ uint32_t sh_drop;       // the next level's queue is full: this block's children are dropped (frame void)
+    // grid-stride over the level: the launch is sized by the host (exact n) or by the queue's capacity
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n_level; base += gridDim.x * blockDim.x) {
+    const uint32_t i = base + threadIdx.x;
+    const bool active = i < n_level;
     bool want_lit = false, want_refl = false, want_trans = false;
     Ray ray, refl, trans;
     D3 hp = d3(0, 0, 0), n = d3(0, 0, 0);
@@ -99,8 +123,6 @@ __global__ void __launch_bounds__(256) k_shade(const DScene s, const LevelBuffer
     // ---- queue compaction: slots by warp ballot + popc, warps ranked inside the block through
     // shared-memory counters, ONE global atomic per block per queue (the per-warp version spent
     // half of this kernel serialised on three L2 addresses).
-    __shared__ uint32_t sh_cnt[3];     // lit, reflection, transmission entries of this block
-    __shared__ uint32_t sh_base[2];    // block base in the lit / next-level queues
     if (threadIdx.x < 3) sh_cnt[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t m_lit = __ballot_sync(0xffffffffu, want_lit);
@@ -116,12 +138,19 @@ __global__ void __launch_bounds__(256) k_shade(const DScene s, const LevelBuffer
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t n_lit_b = sh_cnt[0], n_next_b = sh_cnt[1], n_trans_b = sh_cnt[2];
-        sh_base[0] = n_lit_b ? atomicAdd(&ctr->q_lit, n_lit_b) : 0u;
-        sh_base[1] = n_next_b ? atomicAdd(&ctr->q_next, n_next_b) : 0u;
+        sh_base[0] = n_lit_b ? atomicAdd(lb.q_lit, n_lit_b) : 0u;
+        sh_base[1] = n_next_b ? atomicAdd(lb.q_next, n_next_b) : 0u;
+        sh_drop = 0u;
+        if (n_next_b && (uint64_t)sh_base[1] + n_next_b > lb.cap_next) {   // only possible with device-sized queues
+            sh_drop = 1u;
+            atomicExch(lb.void_flag, 1u);
+        }
         if (n_next_b - n_trans_b) atomicAdd(&ctr->rays[2], (unsigned long long)(n_next_b - n_trans_b));
         if (n_trans_b) atomicAdd(&ctr->rays[3], (unsigned long long)n_trans_b);
+        if (lb.count_on_device && n_lit_b) atomicAdd(&ctr->rays[1], (unsigned long long)n_lit_b * s.n_lights);
     }
     __syncthreads();
+    if (sh_drop) { want_refl = false; want_trans = false; }
     const uint32_t base_lit = sh_base[0] + __shfl_sync(0xffffffffu, w_lit, 0);
     const uint32_t base_next = sh_base[1] + __shfl_sync(0xffffffffu, w_next, 0);
     uint32_t child_refl = kChildDefault, child_trans = kChildDefault;
@@ -155,15 +184,17 @@ __global__ void __launch_bounds__(256) k_shade(const DScene s, const LevelBuffer
         lb.node_a[i] = na;
         lb.node_b[i] = make_uint4(child_refl, child_trans, kind, __float_as_uint(transparency));
     }
+    }   // grid-stride loop
 }
 
 // rendering.rs:140,157-171: final_color accumulates light by light, in scene order, then clamps.
 __global__ void __launch_bounds__(256) k_diffuse(const DScene s, const float4 *__restrict__ lit_bc,
                                                  const uint32_t *__restrict__ lit_node, const float2 *__restrict__ s_ab,
-                                                 const uint8_t *__restrict__ s_lit, float4 *node_a, uint32_t n_lit,
-                                                 uint32_t shadow_sl, uint32_t shadow_sj) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_lit) return;
+                                                 const uint8_t *__restrict__ s_lit, float4 *node_a, uint32_t n_lit_host,
+                                                 uint32_t shadow_sl, uint32_t shadow_sj, const unsigned int *n_lit_dev,
+                                                 const unsigned int *void_flag) {
+    const uint32_t n_lit = level_size(n_lit_host, n_lit_dev, void_flag);
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_lit; j += gridDim.x * blockDim.x) {
     const float4 b = lit_bc[j];
     const C3 bc = c3(b.x, b.y, b.z);
     C3 fin = c3(0.0f, 0.0f, 0.0f);
@@ -177,17 +208,19 @@ __global__ void __launch_bounds__(256) k_diffuse(const DScene s, const float4 *_
     float4 a = node_a[node];
     a.x = fin.r; a.y = fin.g; a.z = fin.b;
     node_a[node] = a;
+    }
 }
 
 // get_color's combination of child colours (rendering.rs:88-93, 112-116), one level at a time,
 // deepest level first.  `child_a` is the (already final) level below.
 __global__ void __launch_bounds__(256) k_combine(const DScene s, float4 *node_a, const uint4 *__restrict__ node_b,
-                                                 const float4 *__restrict__ child_a, uint32_t n) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint4 b = node_b[i];
-    if (b.z != NODE_REFLECTING && b.z != NODE_REFRACTIVE) return;
+                                                 const float4 *__restrict__ child_a, uint32_t n_host,
+                                                 const unsigned int *n_dev, const unsigned int *void_flag) {
+    const uint32_t n = level_size(n_host, n_dev, void_flag);
     const C3 dflt = c3(s.default_color[0], s.default_color[1], s.default_color[2]);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint4 b = node_b[i];
+    if (b.z != NODE_REFLECTING && b.z != NODE_REFRACTIVE) continue;
     float4 a = node_a[i];
     C3 refl = dflt, refr = dflt;
     if (b.x != kChildDefault) { float4 c = child_a[b.x]; refl = c3(c.x, c.y, c.z); }
@@ -201,6 +234,11 @@ __global__ void __launch_bounds__(256) k_combine(const DScene s, float4 *node_a,
     }
     a.x = out.r; a.y = out.g; a.z = out.b;
     node_a[i] = a;
+    }
+}
+
+__device__ __forceinline__ uint32_t pack_rgba(uchar4 c) {
+    return (uint32_t)c.x | ((uint32_t)c.y << 8) | ((uint32_t)c.z << 16) | ((uint32_t)c.w << 24);
 }
 
 // Color::rgba (color.rs:32-37): 4 pixels per thread, one 128-bit store
@@ -208,10 +246,10 @@ __global__ void __launch_bounds__(256) k_quantise(const float4 *__restrict__ nod
     const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
     if (i4 >= npix) return;
     if (i4 + 4u <= npix && (reinterpret_cast<uintptr_t>(out + i4) & 15u) == 0) {
-        uchar4 p[4];
+        uint32_t p[4];   // one packed RGBA8 word per pixel, stored as one 128-bit word
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { float4 a = node_a[i4 + k]; p[k] = quantise(c3(a.x, a.y, a.z)); }
-        *reinterpret_cast<uint4 *>(out + i4) = *reinterpret_cast<uint4 *>(p);
+        for (int k = 0; k < 4; ++k) { float4 a = node_a[i4 + k]; p[k] = pack_rgba(quantise(c3(a.x, a.y, a.z))); }
+        *reinterpret_cast<uint4 *>(out + i4) = make_uint4(p[0], p[1], p[2], p[3]);
     } else {
         for (uint32_t k = i4; k < npix && k < i4 + 4u; ++k) { float4 a = node_a[k]; out[k] = quantise(c3(a.x, a.y, a.z)); }
     }
@@ -228,11 +266,11 @@ __global__ void __launch_bounds__(256) k_quantise_scatter(const float4 *__restri
     const uint32_t r = i4 / width, x = i4 - r * width;
     if (x + 4u <= width && i4 + 4u <= npix) {
         uchar4 *dst = frame + (size_t)rows[row0 + r] * width + x;
-        uchar4 p[4];
+        uint32_t p[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { float4 a = node_a[i4 + k]; p[k] = quantise(c3(a.x, a.y, a.z)); }
-        if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<uint4 *>(p);
-        else { dst[0] = p[0]; dst[1] = p[1]; dst[2] = p[2]; dst[3] = p[3]; }
+        for (int k = 0; k < 4; ++k) { float4 a = node_a[i4 + k]; p[k] = pack_rgba(quantise(c3(a.x, a.y, a.z))); }
+        if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) *reinterpret_cast<uint4 *>(dst) = make_uint4(p[0], p[1], p[2], p[3]);
+        else { uint32_t *d32 = reinterpret_cast<uint32_t *>(dst); d32[0] = p[0]; d32[1] = p[1]; d32[2] = p[2]; d32[3] = p[3]; }
     } else {
         for (uint32_t k = i4; k < npix && k < i4 + 4u; ++k) {
             const uint32_t rk = k / width;
@@ -265,6 +303,12 @@ __global__ void __launch_bounds__(128) k_verify_trace(const DScene s, const Trac
                    ANY ? "shadow" : "path", i, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, h.t, h.body,
                    ANY ? (double)a.out_lit[pi] : a.out_t[pi], ANY ? 0u : a.out_body[pi]);
     }
+}
+
+// shadow-queue order: hit-major (the L rays of a hit adjacent; default) or light-major (experiment)
+static bool shadow_light_major() {
+    static const bool v = [] { const char *e = getenv("RG_SHADOW_LIGHT_MAJOR"); return e && atoi(e) != 0; }();
+    return v;
 }
 
 static RayQueue make_queue(DeviceBuffer &b, size_t cap) {
@@ -314,17 +358,22 @@ static int launch_trace(rg_scene *sc, const TraceArgs &ta, bool use_grid, cudaSt
         const unsigned blocks = std::min<unsigned>(want, (unsigned)(sc->sm_count * bps));
         TraceArgs tuned = ta;
         tuned.g_refill = t_refill; tuned.g_quorum = t_quorum; tuned.g_burst = t_burst;
-        tuned.fetch = ANY ? &ta.ctr->fetch_shadow : &ta.ctr->fetch;   // the two kinds may run concurrently
-        RG_CUDA(cudaMemsetAsync(tuned.fetch, 0, sizeof(unsigned int), stream));
-        k_trace_grid<ANY><<<blocks, kGridTraceThreads, 0, stream>>>(sc->ds, tuned);
+        if (!ta.fetch) {   // (the host-free loop brings a counter per level, zeroed once per batch)
+            tuned.fetch = ANY ? &ta.ctr->fetch_shadow : &ta.ctr->fetch;   // the two kinds may run concurrently
+            RG_CUDA(cudaMemsetAsync(tuned.fetch, 0, sizeof(unsigned int), stream));
+        }
+        if (sc->trace_stats) k_trace_grid<ANY, true><<<blocks, kGridTraceThreads, 0, stream>>>(sc->ds, tuned);
+        else k_trace_grid<ANY, false><<<blocks, kGridTraceThreads, 0, stream>>>(sc->ds, tuned);
     } else if (brute_resident_fits(sc) && ta.n >= (uint32_t)sc->sm_count * 64u * 32u) {
         // the whole cull array fits in one SM's shared memory: one persistent CTA per SM, warps
         // pull ray tiles from a counter and never meet at a barrier again (rg_trace.cuh)
         static const int variant = [] { const char *e = getenv("RG_RESIDENT_VARIANT"); return e ? atoi(e) : 0; }();
         const uint32_t n_records = (uint32_t)(((size_t)sc->ds.n_spheres + 3) / 4 * 4);
         TraceArgs tuned = ta;
-        tuned.fetch = ANY ? &ta.ctr->fetch_shadow : &ta.ctr->fetch;
-        RG_CUDA(cudaMemsetAsync(tuned.fetch, 0, sizeof(unsigned int), stream));
+        if (!ta.fetch) {
+            tuned.fetch = ANY ? &ta.ctr->fetch_shadow : &ta.ctr->fetch;
+            RG_CUDA(cudaMemsetAsync(tuned.fetch, 0, sizeof(unsigned int), stream));
+        }
 #define RG_LAUNCH_RESIDENT(R_, U_, T_, PF_)                                                                                   \
     do {                                                                                                                      \
         static uint64_t attr_set = 0; /* per device: the attribute belongs to the device's copy of the function */          \
@@ -418,7 +467,7 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
     uint32_t n = npix, d = 0;
     if ((rc = wf.ray[0].reserve((size_t)n * 48))) return rc;
     RayQueue cur = make_queue(wf.ray[0], n);
-    k_generate<<<blocks(n), 256, 0, stream>>>(ds, cur, width, height, y0, npix, d_rows);
+    k_generate<<<blocks(n), 256, 0, stream>>>(ds, cur, width, height, y0, npix, d_rows, nullptr);
     RG_CUDA(cudaGetLastError());
     st->gpu_launches++;
     st->rays_primary += npix;
@@ -476,11 +525,15 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
         lb.lit_bc = wf.lit_bc[p].as<float4>();
         lb.lit_node = wf.lit_node[p].as<uint32_t>();
         lb.n = n;
-        // shadow-queue order: hit-major (the L rays of a hit adjacent; default) or light-major
-        static const bool light_major = [] { const char *e = getenv("RG_SHADOW_LIGHT_MAJOR"); return e && atoi(e) != 0; }();
+        const bool light_major = shadow_light_major();
         lb.shadow_sl = light_major ? n : 1u;
         lb.shadow_sj = light_major ? 1u : L;
         lb.can_spawn = can_spawn ? 1u : 0u;
+        lb.q_next = &dc->q_next;
+        lb.q_lit = &dc->q_lit;
+        lb.cap_next = 0xFFFFFFFFu;   // the next queue holds 2n rays: cannot overflow
+        lb.void_flag = &dc->overflow;
+        lb.level = d;
         RG_CUDA(cudaMemsetAsync(&dc->q_next, 0, 2 * sizeof(unsigned int), stream));
         if (shadow_done[p]) RG_CUDA(cudaStreamWaitEvent(stream, shadow_done[p], 0));   // level d-2 still reads these buffers
         k_shade<<<blocks(n), 256, 0, stream>>>(ds, lb, dc);
@@ -539,7 +592,7 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
         }
         if (n_lit) {
             k_diffuse<<<blocks(n_lit), 256, 0, aux>>>(ds, lb.lit_bc, lb.lit_node, lb.s_ab, wf.s_lit[p].as<uint8_t>(),
-                                                      lb.node_a, n_lit, lb.shadow_sl, lb.shadow_sj);
+                                                      lb.node_a, n_lit, lb.shadow_sl, lb.shadow_sj, nullptr, nullptr);
             RG_CUDA(cudaGetLastError());
             st->gpu_launches++;
             if (overlap) {
@@ -561,7 +614,7 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
         float4 *a = wf.nodes[lvl].as<float4>();
         const uint4 *b = reinterpret_cast<const uint4 *>(a + ln);
         const float4 *child = (size_t)lvl + 1 < level_n.size() ? wf.nodes[lvl + 1].as<float4>() : nullptr;
-        k_combine<<<blocks(ln), 256, 0, stream>>>(ds, a, b, child, ln);
+        k_combine<<<blocks(ln), 256, 0, stream>>>(ds, a, b, child, ln, nullptr, nullptr);
         RG_CUDA(cudaGetLastError());
         st->gpu_launches++;
     }
@@ -573,6 +626,262 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
     st->gpu_launches++;
     st->batches++;
     if (level_n.size() > st->max_level + 1) st->max_level = (uint32_t)level_n.size() - 1;
+    return RG_OK;
+}
+
+// ---- the host-free level loop ------------------------------------------------------------------
+// render_image is one call with no per-depth host involvement (rendering.rs:24-38).  Here the
+// whole batch — every level's trace, shade, shadow trace, diffuse, then combine and quantise —
+// is ENQUEUED without a single host synchronisation: each launch reads its level's size from
+// DCounters::lvl[] (written by the level above) and is sized for the queue's CAPACITY; persistent
+// / grid-stride kernels make surplus blocks free.  Queue capacities are fixed up front:
+//     cap[0] = pixels,   cap[d] = min(2 cap[d-1], kLevelGrowth * pixels)
+// (a hit spawns <= 2 rays, so 2 cap[d-1] is exact; real scenes stay far below kLevelGrowth x).  A level
+// that would outgrow its queue sets DCounters::overflow, every later launch of the frame then does
+// nothing, and the host repeats the render with the exact, host-sized loop above (sticky per scene).
+// The launch sequence depends only on (pixels, depth, lights, buffers), so it can be captured
+// once into a CUDA graph and replayed per frame (RG_OPT_GRAPH).
+constexpr uint32_t kLevelGrowth = 2;
+
+struct DevPlan {
+    uint32_t levels = 0;                    // levels 0 .. levels-1 are enqueued
+    uint32_t cap[RG_MAX_DEPTH + 2] = {0};
+};
+
+static int plan_batch_dev(rg_scene *sc, uint32_t npix, DevPlan &plan) {
+    const DScene &ds = sc->ds;
+    const uint32_t L = ds.n_lights;
+    WavefrontScratch &wf = sc->wf;
+    plan.levels = std::max<uint32_t>(ds.max_depth, 1u);
+    uint64_t cap_max[2] = {0, 0}, cap_all = 0;
+    for (uint32_t d = 0; d < plan.levels; ++d) {
+        const uint64_t c = d == 0 ? npix : std::min<uint64_t>(2ull * plan.cap[d - 1], (uint64_t)kLevelGrowth * npix);
+        if (c > 0x7FFFFFFFull || c * std::max<uint32_t>(L, 1u) > 0x7FFFFFFFull) {
+            set_error("level %u could hold more than 2^31 rays; use a smaller batch", d);
+            return RG_E_NOMEM;
+        }
+        plan.cap[d] = (uint32_t)c;
+        cap_max[d & 1] = std::max(cap_max[d & 1], c);
+        cap_all = std::max(cap_all, c);
+    }
+    int rc;
+    if (wf.nodes.size() < plan.levels) wf.nodes.resize(plan.levels);
+    for (uint32_t d = 0; d < plan.levels; ++d)
+        if ((rc = wf.nodes[d].reserve((size_t)plan.cap[d] * 32))) return rc;
+    if ((rc = wf.hit_t.reserve((size_t)cap_all * 8))) return rc;
+    if ((rc = wf.hit_body.reserve((size_t)cap_all * 4))) return rc;
+    for (int p = 0; p < 2; ++p) {
+        const uint64_t c = std::max<uint64_t>(cap_max[p], 1), sc_ = std::max<uint64_t>(c * L, 1);
+        if ((rc = wf.ray[p].reserve((size_t)c * 48))) return rc;
+        if ((rc = wf.sray[p].reserve((size_t)sc_ * 48))) return rc;
+        if ((rc = wf.s_tmax[p].reserve((size_t)sc_ * 8))) return rc;
+        if ((rc = wf.s_ab[p].reserve((size_t)sc_ * 8))) return rc;
+        if ((rc = wf.s_lit[p].reserve((size_t)sc_))) return rc;
+        if ((rc = wf.lit_bc[p].reserve((size_t)c * 16))) return rc;
+        if ((rc = wf.lit_node[p].reserve((size_t)c * 4))) return rc;
+    }
+    return RG_OK;
+}
+
+// Enqueues one batch.  No allocation, no synchronisation, no host read: legal inside a stream capture.
+// `timed` = record CUDA events around the trace launches (not possible while capturing).
+static int enqueue_batch_dev(rg_scene *sc, const DevPlan &plan, uint32_t width, uint32_t height, uint32_t y0, uint32_t npix,
+                             const uint32_t *d_rows, uchar4 *d_out, cudaStream_t stream, rg_stats *st, bool use_grid,
+                             EventPool *events, EventPool &sync_events,
+                             std::vector<std::pair<cudaEvent_t, cudaEvent_t>> *trace_spans) {
+    const DScene &ds = sc->ds;
+    const uint32_t L = ds.n_lights;
+    WavefrontScratch &wf = sc->wf;
+    DCounters *dc = sc->d_counters;
+    int rc;
+    // enough blocks to fill the chip several times over; grid-stride loops do the rest
+    const unsigned max_blocks = (unsigned)sc->sm_count * 16u;
+    auto blocks = [&](uint64_t n) { return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, max_blocks)); };
+    const bool overlap = L > 0 && (sc->overlap == 2 || (sc->overlap == 0 && use_grid));
+    cudaStream_t aux = overlap ? wf.aux : stream;
+    cudaEvent_t shadow_done[2] = {nullptr, nullptr};
+
+    RG_CUDA(cudaMemsetAsync(dc->lvl, 0, sizeof(dc->lvl), stream));
+    RayQueue cur = make_queue(wf.ray[0], plan.cap[0]);
+    k_generate<<<(npix + 255) / 256, 256, 0, stream>>>(ds, cur, width, height, y0, npix, d_rows, &dc->lvl[0].n);
+    RG_CUDA(cudaGetLastError());
+    st->gpu_launches++;
+    st->rays_primary += npix;
+
+    for (uint32_t d = 0; d < plan.levels; ++d) {
+        const bool can_spawn = d + 1 < ds.max_depth;
+        const uint32_t cap = plan.cap[d], cap_next = can_spawn ? plan.cap[d + 1] : 0u;
+        const int p = overlap ? (int)(d & 1u) : 0;
+        TraceArgs ta{};
+        ta.q = cur;
+        ta.n = cap;
+        ta.n_dev = &dc->lvl[d].n;
+        ta.n_mul = 1;
+        ta.void_flag = &dc->overflow;
+        ta.fetch = &dc->lvl[d].fetch;
+        ta.out_t = wf.hit_t.as<double>();
+        ta.out_body = wf.hit_body.as<uint32_t>();
+        ta.ctr = dc;
+        ta.verify = sc->verify_cull == 1;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (events) { e0 = events->get(); e1 = events->get(); RG_CUDA(cudaEventRecord(e0, stream)); }
+        if ((rc = launch_trace<false>(sc, ta, use_grid, stream))) return rc;
+        if (events) { RG_CUDA(cudaEventRecord(e1, stream)); trace_spans->emplace_back(e0, e1); }
+        st->gpu_launches++;
+
+        LevelBuffers lb{};
+        lb.cur = cur;
+        lb.next = make_queue(wf.ray[(d + 1) & 1], std::max<uint32_t>(cap_next, 1u));
+        lb.shadow = make_queue(wf.sray[p], (size_t)std::max<uint64_t>((uint64_t)cap * L, 1));
+        lb.hit_t = wf.hit_t.as<double>();
+        lb.hit_body = wf.hit_body.as<uint32_t>();
+        lb.node_a = wf.nodes[d].as<float4>();
+        lb.node_b = reinterpret_cast<uint4 *>(wf.nodes[d].as<float4>() + cap);
+        lb.s_tmax = wf.s_tmax[p].as<double>();
+        lb.s_ab = wf.s_ab[p].as<float2>();
+        lb.lit_bc = wf.lit_bc[p].as<float4>();
+        lb.lit_node = wf.lit_node[p].as<uint32_t>();
+        lb.n = cap;
+        lb.n_dev = &dc->lvl[d].n;
+        lb.shadow_sl = 1u;    // hit-major shadow queue
+        lb.shadow_sj = L;
+        lb.can_spawn = can_spawn ? 1u : 0u;
+        lb.q_next = &dc->lvl[d + 1].n;
+        lb.q_lit = &dc->lvl[d].n_lit;
+        lb.cap_next = cap_next;
+        lb.void_flag = &dc->overflow;
+        lb.level = d;
+        lb.count_on_device = 1u;
+        if (shadow_done[p]) RG_CUDA(cudaStreamWaitEvent(stream, shadow_done[p], 0));   // level d-2 still reads these buffers
+        k_shade<<<blocks(cap), 256, 0, stream>>>(ds, lb, dc);
+        RG_CUDA(cudaGetLastError());
+        st->gpu_launches++;
+
+        if (L) {   // shadow side, concurrent with the next level's path side
+            if (overlap) {
+                cudaEvent_t shaded = sync_events.get();
+                RG_CUDA(cudaEventRecord(shaded, stream));
+                RG_CUDA(cudaStreamWaitEvent(aux, shaded, 0));
+            }
+            TraceArgs sa{};
+            sa.q = lb.shadow;
+            sa.tmax = lb.s_tmax;
+            sa.n = cap * L;
+            sa.n_dev = &dc->lvl[d].n_lit;
+            sa.n_mul = L;
+            sa.void_flag = &dc->overflow;
+            sa.fetch = &dc->lvl[d].fetch_shadow;
+            sa.out_lit = wf.s_lit[p].as<uint8_t>();
+            sa.ctr = dc;
+            sa.verify = sc->verify_cull == 1;
+            if (events) { e0 = events->get(); e1 = events->get(); RG_CUDA(cudaEventRecord(e0, aux)); }
+            if ((rc = launch_trace<true>(sc, sa, use_grid, aux))) return rc;
+            if (events) { RG_CUDA(cudaEventRecord(e1, aux)); trace_spans->emplace_back(e0, e1); }
+            st->gpu_launches++;
+        }
+        k_diffuse<<<blocks(cap), 256, 0, aux>>>(ds, lb.lit_bc, lb.lit_node, lb.s_ab, wf.s_lit[p].as<uint8_t>(), lb.node_a, cap,
+                                                lb.shadow_sl, lb.shadow_sj, &dc->lvl[d].n_lit, &dc->overflow);
+        RG_CUDA(cudaGetLastError());
+        st->gpu_launches++;
+        if (overlap) {
+            shadow_done[p] = sync_events.get();
+            RG_CUDA(cudaEventRecord(shadow_done[p], aux));
+        }
+        cur = lb.next;
+    }
+    for (int q = 0; q < 2; ++q)
+        if (shadow_done[q]) RG_CUDA(cudaStreamWaitEvent(stream, shadow_done[q], 0));
+    for (int lvl = (int)plan.levels - 1; lvl >= 0; --lvl) {
+        float4 *a = wf.nodes[lvl].as<float4>();
+        const uint4 *b = reinterpret_cast<const uint4 *>(a + plan.cap[lvl]);
+        const float4 *child = (uint32_t)lvl + 1 < plan.levels ? wf.nodes[lvl + 1].as<float4>() : nullptr;
+        k_combine<<<blocks(plan.cap[lvl]), 256, 0, stream>>>(ds, a, b, child, plan.cap[lvl], &dc->lvl[lvl].n, &dc->overflow);
+        RG_CUDA(cudaGetLastError());
+        st->gpu_launches++;
+    }
+    if (sc->scatter_out)
+        k_quantise_scatter<<<(unsigned)((((uint64_t)npix + 3) / 4 + 255) / 256), 256, 0, stream>>>(wf.nodes[0].as<float4>(), d_out, npix, width, d_rows, y0);
+    else
+        k_quantise<<<(unsigned)((((uint64_t)npix + 3) / 4 + 255) / 256), 256, 0, stream>>>(wf.nodes[0].as<float4>(), d_out, npix);
+    RG_CUDA(cudaGetLastError());
+    st->gpu_launches++;
+    st->batches++;
+    return RG_OK;
+}
+
+// ---- one CUDA graph per batch shape --------------------------------------------------------------
+static std::vector<uint64_t> graph_key(const rg_scene *sc, const DevPlan &plan, uint32_t width, uint32_t height, uint32_t y0,
+                                       uint32_t npix, const uint32_t *d_rows, const uchar4 *d_out, bool use_grid) {
+    const WavefrontScratch &wf = sc->wf;
+    std::vector<uint64_t> k = {width, height, y0, npix, (uint64_t)(uintptr_t)d_rows, (uint64_t)(uintptr_t)d_out,
+                               (uint64_t)use_grid, (uint64_t)sc->scatter_out, (uint64_t)sc->ds.max_depth, (uint64_t)sc->overlap,
+                               (uint64_t)sc->verify_cull, (uint64_t)sc->trace_stats, (uint64_t)plan.levels};
+    auto add = [&](const DeviceBuffer &b) { k.push_back((uint64_t)(uintptr_t)b.ptr); };
+    add(wf.ray[0]); add(wf.ray[1]); add(wf.hit_t); add(wf.hit_body);
+    for (int p = 0; p < 2; ++p) { add(wf.sray[p]); add(wf.s_tmax[p]); add(wf.s_ab[p]); add(wf.s_lit[p]); add(wf.lit_bc[p]); add(wf.lit_node[p]); }
+    for (uint32_t d = 0; d < plan.levels; ++d) add(wf.nodes[d]);
+    return k;
+}
+
+// Replays the batch from a captured graph; captures it when its key is seen for the second time.
+// Returns RG_OK with *done = false when the batch should be enqueued the ordinary way.
+static int graph_batch(rg_scene *sc, const DevPlan &plan, uint32_t width, uint32_t height, uint32_t y0, uint32_t npix,
+                       const uint32_t *d_rows, uchar4 *d_out, cudaStream_t stream, rg_stats *st, bool use_grid,
+                       EventPool &sync_events, bool *done) {
+    *done = false;
+    GraphCache &gc = sc->graphs;
+    const std::vector<uint64_t> key = graph_key(sc, plan, width, height, y0, npix, d_rows, d_out, use_grid);
+    GraphEntry *hit = nullptr;
+    for (auto &e : gc.entries)
+        if (e.key == key) { hit = &e; break; }
+    if (!hit) {
+        bool seen = false;
+        for (auto &k : gc.seen) seen = seen || k == key;
+        if (!seen) {   // first time: run it eagerly (also warms every lazily initialised launch path)
+            if (gc.seen.size() >= 32) gc.seen.erase(gc.seen.begin());
+            gc.seen.push_back(key);
+            return RG_OK;
+        }
+        // capture on the library's own stream (the caller's may be the legacy stream, which cannot capture)
+        cudaStream_t cs = sc->stream;
+        rg_stats tmp{};
+        const size_t sync_used = sync_events.used;
+        RG_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_batch_dev(sc, plan, width, height, y0, npix, d_rows, d_out, cs, &tmp, use_grid, nullptr, sync_events, nullptr);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        sync_events.used = sync_used;
+        if (rc != RG_OK || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            sc->graph = 1;   // capture is not possible here: stay with eager launches
+            return rc != RG_OK ? rc : RG_OK;
+        }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { cudaGetLastError(); sc->graph = 1; return RG_OK; }
+        if (gc.entries.size() >= 8) {   // evict the least recently used
+            size_t lru = 0;
+            for (size_t i = 1; i < gc.entries.size(); ++i)
+                if (gc.entries[i].last_use < gc.entries[lru].last_use) lru = i;
+            cudaGraphExecDestroy(gc.entries[lru].exec);
+            gc.entries.erase(gc.entries.begin() + (long)lru);
+        }
+        GraphEntry e;
+        e.key = key;
+        e.exec = exec;
+        e.launches = tmp.gpu_launches;
+        gc.entries.push_back(std::move(e));
+        hit = &gc.entries.back();
+    }
+    hit->last_use = ++gc.tick;
+    RG_CUDA(cudaGraphLaunch(hit->exec, stream));
+    st->gpu_launches += hit->launches;
+    st->rays_primary += npix;
+    st->batches++;
+    st->graph_replays++;
+    *done = true;
     return RG_OK;
 }
 
@@ -592,6 +901,9 @@ int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0,
     uint32_t batch_rows = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(rows ? rows : 1, batch_pixels / width));
     const rg_stats st0 = *st;
     for (;;) {   // a ray tree larger than device memory restarts the render with half the rows per batch
+        // host-free loop (device-sized launches, no synchronisation inside the frame) unless switched off,
+        // or this scene once outgrew the default queue capacities, or a debug mode needs the host in the loop
+        const bool host_free = sc->host_free != 1 && !sc->host_free_overflowed && sc->verify_cull < 2 && !shadow_light_major();
         *st = st0;
         events.used = 0;
         sync_events.used = 0;
@@ -599,10 +911,26 @@ int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0,
         RG_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(DCounters), stream));
         RG_CUDA(cudaEventRecord(sc->ev[0], stream));
         int rc = RG_OK;
+        if (host_free && sc->ds.n_lights > 0 && (sc->overlap == 2 || (sc->overlap == 0 && use_grid)) && !sc->wf.aux)
+            RG_CUDA(cudaStreamCreateWithFlags(&sc->wf.aux, cudaStreamNonBlocking));
         for (uint32_t y = y0; y < y1 && rc == RG_OK;) {
             const uint32_t ye = (uint32_t)std::min<uint64_t>((uint64_t)y + batch_rows, y1);
-            rc = render_batch(sc, width, height, y, ye, d_rows, sc->scatter_out ? d_out : d_out + (size_t)(y - y0) * width, stream, st, use_grid,
-                              events, sync_events, trace_spans);
+            uchar4 *out = sc->scatter_out ? d_out : d_out + (size_t)(y - y0) * width;
+            if (host_free) {
+                DevPlan plan;
+                const uint64_t npix64 = (uint64_t)(ye - y) * width;
+                if (npix64 > 0x7FFFFFFFull) { set_error("batch of %llu pixels is too large", (unsigned long long)npix64); rc = RG_E_NOMEM; }
+                else if (npix64 && (rc = plan_batch_dev(sc, (uint32_t)npix64, plan)) == RG_OK) {
+                    bool done = false;
+                    if (sc->graph != 1 && sc->verify_cull == 0)
+                        rc = graph_batch(sc, plan, width, height, y, (uint32_t)npix64, d_rows, out, stream, st, use_grid, sync_events, &done);
+                    if (rc == RG_OK && !done)
+                        rc = enqueue_batch_dev(sc, plan, width, height, y, (uint32_t)npix64, d_rows, out, stream, st, use_grid, &events,
+                                               sync_events, &trace_spans);
+                }
+            } else {
+                rc = render_batch(sc, width, height, y, ye, d_rows, out, stream, st, use_grid, events, sync_events, trace_spans);
+            }
             y = ye;
         }
         if (rc == RG_E_NOMEM && batch_rows > 1) {
@@ -614,11 +942,16 @@ int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0,
             continue;
         }
         if (rc) return rc;
+        RG_CUDA(cudaEventRecord(sc->ev[1], stream));
+        RG_CUDA(cudaMemcpyAsync(sc->h_counters, sc->d_counters, sizeof(DCounters), cudaMemcpyDeviceToHost, stream));
+        RG_CUDA(cudaStreamSynchronize(stream));
+        if (host_free && sc->h_counters->overflow) {   // a level outgrew its queue: repeat with exact, host-sized queues
+            sc->host_free_overflowed = true;
+            continue;
+        }
         break;
     }
-    RG_CUDA(cudaEventRecord(sc->ev[1], stream));
-    RG_CUDA(cudaMemcpyAsync(sc->h_counters, sc->d_counters, sizeof(DCounters), cudaMemcpyDeviceToHost, stream));
-    RG_CUDA(cudaStreamSynchronize(stream));
+    st->host_free = (sc->host_free != 1 && !sc->host_free_overflowed && sc->verify_cull < 2 && !shadow_light_major()) ? 1u : 0u;
     float ms = 0.f;
     RG_CUDA(cudaEventElapsedTime(&ms, sc->ev[0], sc->ev[1]));
     st->ms_device = ms;
@@ -629,6 +962,14 @@ int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0,
     }
     st->ms_trace = tr;
     const DCounters &c = *sc->h_counters;
+    st->rays_shadow += c.rays[1];                        // host-free loop: counted on the device
+    if (c.max_level > st->max_level) st->max_level = c.max_level;
+    st->grid_cells = c.grid_cells;
+    st->grid_fetches = c.grid_fetches;
+    st->grid_culls = c.grid_culls;
+    st->grid_refills = c.grid_refills;
+    st->grid_lane_steps = c.grid_lane_steps;
+    st->grid_lane_slots = c.grid_lane_slots;
     st->rays_reflection = c.rays[2];
     st->rays_transmission = c.rays[3];
     st->exact_tests = c.exact_tests;

@@ -33,7 +33,7 @@ BODY_SPHERE, BODY_PLANE, BODY_DISK, BODY_AABB = 0, 1, 2, 3
 COLORATION_COLOR, COLORATION_TEXTURE = 0, 1
 SURFACE_DIFFUSE, SURFACE_REFLECTING, SURFACE_REFRACTIVE = 0, 1, 2
 LIGHT_DIRECTIONAL, LIGHT_SPHERICAL = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class SceneError(ValueError):
@@ -96,6 +96,14 @@ class Stats(ctypes.Structure):
         ("batches", ctypes.c_uint32),
         ("max_level", ctypes.c_uint32),
         ("accel_used", ctypes.c_uint32),
+        ("host_free", ctypes.c_uint32),
+        ("graph_replays", ctypes.c_uint32),
+        ("grid_cells", ctypes.c_uint64),
+        ("grid_fetches", ctypes.c_uint64),
+        ("grid_culls", ctypes.c_uint64),
+        ("grid_refills", ctypes.c_uint64),
+        ("grid_lane_steps", ctypes.c_uint64),
+        ("grid_lane_slots", ctypes.c_uint64),
     ]
 
     @property

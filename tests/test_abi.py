@@ -37,7 +37,7 @@ def test_struct_layouts_match_header():
     assert SceneDesc.n_bodies.offset == 28 and SceneDesc.body_kind.offset == 32
     assert SceneDesc.n_lights.offset == 104 and SceneDesc.light_kind.offset == 112
     assert SceneDesc.textures.offset == 144 and ctypes.sizeof(SceneDesc) == 152
-    assert ctypes.sizeof(Stats) == 120
+    assert ctypes.sizeof(Stats) == 176
 
 
 def test_validation_without_device():

@@ -94,6 +94,61 @@ def test_small_batches_equal_one_batch():
     assert np.array_equal(tiled, full)
 
 
+def test_host_free_loop_graph_replay_and_host_sized_loop_agree(oracle):
+    """The level loop without host involvement (device-sized launches, RG_OPT_HOST_FREE), its CUDA-graph
+    replay (the third identical frame is a replay) and the host-sized loop produce the same bytes and ray
+    counts, on a grid scene and on a brute-force one, for a full frame, a row band and a scattered row list."""
+    import torch
+
+    for name, data, w, h in (("C4-small", make_scene("C4", spheres=400, depth=8)[0], 256, 144),
+                             ("test1", example_scene("test1"), 200, 150)):
+        ref, ost, _ = oracle.render(data, w, h)
+        with rg.Scene(data) as sc:
+            for it in range(4):
+                img = sc.render_image(w, h)
+                st = sc.last_stats
+                _assert_same(img, ref, st, ost, f"{name}/host-free frame {it}")
+                assert st.host_free == 1
+                assert st.graph_replays == (1 if it >= 1 else 0), (name, it, st.graph_replays)
+            band = sc.render_rows(w, h, 17, 90)
+            assert np.array_equal(band, ref[17:90])
+            rows = np.array([h - 1, 0, 5, 6, 7, 40], np.uint32)
+            out = torch.empty(rows.size * w * 4, dtype=torch.uint8, device="cuda")
+            for _ in range(3):   # eager, capture, replay
+                sc.render_rowlist_device(w, h, rows, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                assert np.array_equal(out.cpu().numpy().reshape(rows.size, w, 4), ref[rows])
+            sc.set_option(rg._native.OPT_GRAPH, 1)
+            img = sc.render_image(w, h)
+            assert sc.last_stats.graph_replays == 0 and sc.last_stats.host_free == 1
+            assert np.array_equal(img, ref)
+            sc.set_option(rg._native.OPT_HOST_FREE, 1)
+            img = sc.render_image(w, h)
+            _assert_same(img, ref, sc.last_stats, ost, f"{name}/host-sized")
+            assert sc.last_stats.host_free == 0
+
+
+def test_host_free_queue_overflow_falls_back_to_exact_queues(oracle):
+    """Device-sized queues hold at most 2x the pixels per level.  Nested glass spheres around the camera
+    double the rays at every level (reflection stays inside, transmission meets the next shell), so
+    level 2 outgrows its queue: the device flags it, the library repeats the frame with host-sized
+    (exact) queues and stays there for this scene; the image must still be the oracle's."""
+    from raingun_b200.scene import scene_from_dict
+
+    glass = lambda r: {"Sphere": {"center": [0.0, 0.0, 0.0], "radius": r, "material": {
+        "coloration": {"Color": "#e0f0ff"}, "albedo": 0.5, "surface": {"Refractive": {"index": 1.3, "transparency": 0.95}}}}}
+    doc = {"maxRecursionDepth": 5, "lights": [{"Spherical": {"position": [0.5, 0.5, 0.5], "color": "#ffffff", "intensity": 50.0}}],
+           "bodies": [glass(1.0), glass(2.0), glass(4.0), glass(8.0), glass(16.0)]}
+    data = scene_from_dict(doc)
+    w, h = 160, 90
+    ref, ost, _ = oracle.render(data, w, h)
+    assert ost.rays_reflection + ost.rays_transmission > 6 * w * h   # the tree really doubles
+    with rg.Scene(data) as sc:
+        for it in range(2):
+            img = sc.render_image(w, h)
+            _assert_same(img, ref, sc.last_stats, ost, f"overflow frame {it}")
+            assert sc.last_stats.host_free == 0
+
+
 def test_depth_limit_like_draft(oracle):
     """src/main.rs:74-75,119-123: --draft lowers max_recursion_depth to 4; depth 0 still traces
     the primary ray (rendering.rs:71-78) and returns default_color for every child."""
