@@ -438,6 +438,7 @@ def main() -> int:
             fp32_peak, fp64_peak, _ = rg.measure_peaks(local_rank)
             sc = rg.Scene(data, device=local_rank)
             sc.set_accel(rg.ACCEL_BRUTE)
+            sc.set_option(_native.OPT_GRAPH, 1)   # eager launches: the trace kernels are timed one by one with CUDA events
             bsteps = max(1, min(3, args.steps))
             sc.render_rows_device(w, h, 0, h, staging.data_ptr(), sptr)
             torch.cuda.synchronize(device)

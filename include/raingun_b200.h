@@ -132,8 +132,10 @@ enum {
                                 synchronisation per frame; render_image is one call, rendering.rs:24-38):
                                 0 = automatic (on), 1 = off (host reads every level's size), 2 = on */
     RG_OPT_GRAPH = 8,        /* replay the host-free frame as one CUDA graph: 0 = automatic, 1 = off, 2 = on */
-    RG_OPT_TRACE_STATS = 9   /* 1 = the grid tracer counts cells / fetches / cull tests / lane use
+    RG_OPT_TRACE_STATS = 9,  /* 1 = the grid tracer counts cells / fetches / cull tests / lane use
                                 (rg_stats.grid_*); an instrumented kernel, slower; results unchanged */
+    RG_OPT_REORDER = 10      /* bin every level's children by origin region and direction octant before they
+                                are traced (host-free loop, grid tracer): 0 = automatic (on), 1 = off, 2 = on */
 };
 
 /* Counters and timings of one render call.  A "ray" is one `Scene::trace`

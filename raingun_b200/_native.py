@@ -12,7 +12,8 @@ from typing import Optional
 from .scene import SceneDesc, Stats
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libraingun_b200.so")
+# RAINGUN_B200_LIB selects another build of the same library (tuning experiments: tools/build_variants.sh)
+LIB_PATH = os.environ.get("RAINGUN_B200_LIB") or os.path.join(_HERE, "libraingun_b200.so")
 
 RG_OK = 0
 ERRORS = {0: "RG_OK", -1: "RG_E_INVALID", -2: "RG_E_PORTRAIT", -3: "RG_E_TOO_LARGE", -4: "RG_E_DEPTH",
@@ -22,7 +23,7 @@ E_INVALID, E_PORTRAIT, E_TOO_LARGE, E_DEPTH, E_CUDA, E_NOMEM, E_CANCELLED, E_LIG
 PIPELINE_WAVEFRONT, PIPELINE_MEGAKERNEL = 0, 1
 ACCEL_AUTO, ACCEL_BRUTE, ACCEL_GRID = 0, 1, 2
 OPT_PIPELINE, OPT_ACCEL, OPT_MAX_DEPTH, OPT_BATCH_PIXELS, OPT_VERIFY_CULL, OPT_OVERLAP = 1, 2, 3, 4, 5, 6
-OPT_HOST_FREE, OPT_GRAPH, OPT_TRACE_STATS = 7, 8, 9
+OPT_HOST_FREE, OPT_GRAPH, OPT_TRACE_STATS, OPT_REORDER = 7, 8, 9, 10
 
 ROWS_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                            ctypes.POINTER(ctypes.c_uint8), ctypes.c_void_p)

@@ -114,19 +114,27 @@ static int grid_build_host(rg_scene *sc, const std::vector<double> &sph, const s
     }
     std::sort(loose.begin(), loose.end());
 
-    // Inline cell records: the first two items of every cell live IN the cell's 48-byte record
-    // (their cull records + indices), so a cell visit is one fixed-size fetch and two culls for
-    // every lane; only cells with more than two items (a few per cent at the default density) touch the
-    // overflow lists above.  Empty slots hold a record that every cullable ray rejects.
+    // Cell records: the items of a cell live IN 48-byte records (two cull records + their sphere indices +
+    // the index of the cell's next record), so a visit is one fixed-size fetch and two culls for every
+    // lane.  Record c is cell c's first; a cell with more than two items (a few per cent at the default
+    // density) continues in chained records behind the cells' own (grid_chain_record), which the tracer reads
+    // exactly like a first record: one instruction stream for every scanning lane, no separate overflow
+    // path.  Empty slots hold a record that every cullable ray rejects.
     const float kInf = std::numeric_limits<float>::infinity();
-    std::vector<float4> recs(ncells * 3);
+    const size_t nrecs = grid_record_count(ncells, start[ncells]);
+    std::vector<float4> recs(nrecs * 3, make_float4(0.f, 0.f, 0.f, kInf));
     for (size_t c = 0; c < ncells; ++c) {
-        const uint32_t b0 = start[c], b1 = start[c + 1], n = b1 - b0;
-        recs[3 * c] = n > 0 ? items_cull[b0] : make_float4(0.f, 0.f, 0.f, kInf);
-        recs[3 * c + 1] = n > 1 ? items_cull[b0 + 1] : make_float4(0.f, 0.f, 0.f, kInf);
-        uint4 meta = make_uint4(n > 0 ? items[b0] : 0xFFFFFFFFu, n > 1 ? items[b0 + 1] : 0xFFFFFFFFu,
-                                n > 2 ? b0 + 2 : 0u, n > 2 ? b1 : 0u);
-        std::memcpy(&recs[3 * c + 2], &meta, sizeof(meta));
+        const uint32_t b0 = start[c], b1 = start[c + 1];
+        for (uint32_t pos = b0, r = (uint32_t)c; pos < b1 || pos == b0; pos += 2) {   // every cell has its first record, even when empty
+            const uint32_t n = b1 - pos > 2 ? 2 : b1 - pos;
+            const uint32_t next = pos + 2 < b1 ? grid_chain_record((uint32_t)ncells, pos + 2) : 0u;
+            recs[3 * (size_t)r] = n > 0 ? items_cull[pos] : make_float4(0.f, 0.f, 0.f, kInf);
+            recs[3 * (size_t)r + 1] = n > 1 ? items_cull[pos + 1] : make_float4(0.f, 0.f, 0.f, kInf);
+            const uint4 meta = make_uint4(n > 0 ? items[pos] : 0xFFFFFFFFu, n > 1 ? items[pos + 1] : 0xFFFFFFFFu, next, 0u);
+            std::memcpy(&recs[3 * (size_t)r + 2], &meta, sizeof(meta));
+            r = next;
+            if (!next) break;
+        }
     }
 
     int rc;
@@ -285,11 +293,16 @@ __global__ void __launch_bounds__(256) k_gb_finish(uint32_t ncells, const uint32
     gb_sort_u32(items + b0, n);   // lists are short (mean < 1, rarely > 8)
     for (uint32_t i = b0; i < b1; ++i) items_cull[i] = cull4[items[i]];
     const float kInf = __int_as_float(0x7f800000);
-    recs[3 * (size_t)c] = n > 0 ? items_cull[b0] : make_float4(0.f, 0.f, 0.f, kInf);
-    recs[3 * (size_t)c + 1] = n > 1 ? items_cull[b0 + 1] : make_float4(0.f, 0.f, 0.f, kInf);
-    const uint4 meta = make_uint4(n > 0 ? items[b0] : 0xFFFFFFFFu, n > 1 ? items[b0 + 1] : 0xFFFFFFFFu, n > 2 ? b0 + 2 : 0u,
-                                  n > 2 ? b1 : 0u);
-    *reinterpret_cast<uint4 *>(&recs[3 * (size_t)c + 2]) = meta;
+    for (uint32_t pos = b0, r = c;; pos += 2) {   // the cell's chain of records (see grid_build_host)
+        const uint32_t m = b1 - pos > 2 ? 2 : b1 - pos;
+        const uint32_t next = pos + 2 < b1 ? grid_chain_record(ncells, pos + 2) : 0u;
+        recs[3 * (size_t)r] = m > 0 ? items_cull[pos] : make_float4(0.f, 0.f, 0.f, kInf);
+        recs[3 * (size_t)r + 1] = m > 1 ? items_cull[pos + 1] : make_float4(0.f, 0.f, 0.f, kInf);
+        *reinterpret_cast<uint4 *>(&recs[3 * (size_t)r + 2]) =
+            make_uint4(m > 0 ? items[pos] : 0xFFFFFFFFu, m > 1 ? items[pos + 1] : 0xFFFFFFFFu, next, 0u);
+        if (!next) break;
+        r = next;
+    }
 }
 
 __global__ void k_gb_sort_loose(const uint32_t *tmp, uint32_t n, uint32_t *out) {   // n <= 256: one thread
@@ -348,8 +361,7 @@ static int grid_build_device(rg_scene *sc, const std::vector<double> &sph) {
     uint32_t *cursor = static_cast<uint32_t *>(sc->arena.alloc(ncells * sizeof(uint32_t)));
     uint32_t *ctr = static_cast<uint32_t *>(sc->arena.alloc(4 * sizeof(uint32_t)));
     uint32_t *loose_tmp = static_cast<uint32_t *>(sc->arena.alloc(kGbLooseTmp * sizeof(uint32_t)));
-    float4 *recs = static_cast<float4 *>(sc->arena.alloc(ncells * 3 * sizeof(float4)));
-    if (!start || !cursor || !ctr || !loose_tmp || !recs) return RG_E_NOMEM;
+    if (!start || !cursor || !ctr || !loose_tmp) return RG_E_NOMEM;
     cudaStream_t st = sc->stream;
     RG_CUDA(cudaMemsetAsync(start, 0, (ncells + 1) * sizeof(uint32_t), st));
     RG_CUDA(cudaMemsetAsync(cursor, 0, ncells * sizeof(uint32_t), st));
@@ -366,7 +378,8 @@ static int grid_build_device(rg_scene *sc, const std::vector<double> &sph) {
     uint32_t *items = static_cast<uint32_t *>(sc->arena.alloc((size_t)std::max<uint32_t>(total, 1) * sizeof(uint32_t)));
     float4 *items_cull = static_cast<float4 *>(sc->arena.alloc((size_t)std::max<uint32_t>(total, 1) * sizeof(float4)));
     uint32_t *loose = static_cast<uint32_t *>(sc->arena.alloc((size_t)std::max<uint32_t>(n_loose, 1) * sizeof(uint32_t)));
-    if (!items || !items_cull || !loose) return RG_E_NOMEM;
+    float4 *recs = static_cast<float4 *>(sc->arena.alloc(grid_record_count(ncells, total) * 3 * sizeof(float4)));
+    if (!items || !items_cull || !loose || !recs) return RG_E_NOMEM;
     k_gb_fill<<<sblocks, 256, 0, st>>>(p, sc->ds.sph, start, cursor, items);
     k_gb_finish<<<(unsigned)((ncells + 255) / 256), 256, 0, st>>>((uint32_t)ncells, start, items, sc->ds.cull4, items_cull, recs);
     if (n_loose) k_gb_sort_loose<<<1, 32, 0, st>>>(loose_tmp, n_loose, loose);

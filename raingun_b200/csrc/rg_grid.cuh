@@ -40,15 +40,18 @@ constexpr double kGridUnitTol = 1e-9;
 constexpr int kGridRefill = 12;             // refill when at least this many lanes are idle
 constexpr int kGridExactQuorum = 10;        // evaluate pending candidates when this many lanes wait
 constexpr int kGridScanBurst = 4;           // scan steps between quorum checks
-#ifndef RG_GRID_PREFETCH
-#define RG_GRID_PREFETCH 0
-#endif
 #ifndef RG_GRID_MINB
 #define RG_GRID_MINB 6
 #endif
-constexpr bool kGridPrefetch = RG_GRID_PREFETCH != 0;   // speculative fetch of the next cell's record
 constexpr uint32_t kNoSphere = 0xFFFFFFFFu;
 constexpr float kFltBig = 3.4e38f;
+#define kFltInf __int_as_float(0x7f800000)
+
+// Chained cell records (rg_grid.cu): the record that holds item list positions pos, pos + 1 of a cell whose
+// first two items sit in the cell's own record.  Positions of different cells never share a pair, so
+// ncells + pos / 2 is collision-free and needs no allocation pass.
+__host__ __device__ inline uint32_t grid_chain_record(uint32_t ncells, uint32_t pos) { return ncells + (pos >> 1); }
+__host__ __device__ inline size_t grid_record_count(size_t ncells, size_t total_items) { return ncells + total_items / 2 + 1; }
 
 template <bool ANY>
 struct GridHit {
@@ -95,24 +98,23 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
     uint32_t pi = 0;            // physical queue index of the ray
     CullRay cr;
     GridHit<ANY> h;
-    float ogx = 0, ogy = 0, ogz = 0, ix = 0, iy = 0, iz = 0;   // grid-space origin, 1 / direction
-    float fbx = 0, fby = 0, fbz = 0;                           // next cell boundary per axis (grid coords)
-    float tnx = 0, tny = 0, tnz = 0;                           // ray parameter at those boundaries
-    float sxf = 0, syf = 0, szf = 0;                           // +-1 step per axis (0: never steps)
+    // 3-D DDA, per axis: the ray parameter at the next cell boundary is  tn = tex + k * dt  (ONE fmaf, never
+    // accumulated), where tex = parameter at the grid's exit plane of that axis, dt = |1 / direction| and
+    // -k = boundaries still ahead of the exit plane (a float counter: k > 0 after a step = left the grid)
+    float tnx = 0, tny = 0, tnz = 0;
+    float kx = 0, ky = 0, kz = 0;
+    float dtx = 0, dty = 0, dtz = 0;
+    float tex = 0, tey = 0, tez = 0;
+    float tcur = 0;                                            // parameter at which the walk enters `cell` (+inf: it has left the grid)
+    float boundf = 0;                                          // distances worth looking at, in walk parameter units (FP32, rounded up)
     float t0f = 0;                                             // the walk is parameterised from o + t0*d (far origins)
-    int cx = 0, cy = 0, cz = 0;
-    int cell = 0, scx = 0, scy = 0, scz = 0;                   // linear cell index and its per-axis stride (signed)
+    int cell = 0, scx = 0, scy = 0, scz = 0;                   // linear index of the next cell to examine, per-axis stride (signed)
     uint32_t pend0 = kNoSphere, pend1 = kNoSphere;             // cull survivors waiting for their exact test
-    bool fresh = false;                                        // the current cell's record has not been examined yet
-    uint32_t ok = 0, oe = 0;                                   // cursor / end of the current cell's overflow list
-    float4 c0, c1, n0, n1;                                     // cull records of the current / prefetched next cell
-    uint4 cm, nm;                                              // ... and their (idx0, idx1, overflow begin, end)
+    uint32_t chain = 0;                                        // next record of the cell being examined (0: none, enter the next cell)
     bool exhausted = false;                                    // warp-uniform: the queue has no more rays
     h.best.init();
     h.occluded = false;
     h.tmax = 0.0;
-    c0 = c1 = n0 = n1 = make_float4(0.f, 0.f, 0.f, 0.f);
-    cm = nm = make_uint4(kNoSphere, kNoSphere, 0u, 0u);
     {
         Ray none;
         none.o = d3(0, 0, 0);
@@ -121,26 +123,13 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
     }
 
 
-    // Speculative fetch of the record of the cell the walk would enter next (the axis choice
-    // depends only on the boundary parameters, not on the outcome of the current cell's tests),
-    // so the dependent-load latency of a step overlaps the culls / exact tests of this cell.
-    auto prefetch_next = [&]() {
-        if (!kGridPrefetch) return;
-        const bool ax = tnx <= tny && tnx <= tnz;
-        const bool ay = !ax && tny <= tnz;
-        const int ncx = cx + (ax ? (int)sxf : 0), ncy = cy + (ay ? (int)syf : 0), ncz = cz + ((!ax && !ay) ? (int)szf : 0);
-        const bool inside = (unsigned)ncx < (unsigned)g.dim[0] && (unsigned)ncy < (unsigned)g.dim[1] &&
-                            (unsigned)ncz < (unsigned)g.dim[2];
-        if (inside) {
-            const float4 *rec = g.cell_rec + 3 * (size_t)(cell + (ax ? scx : (ay ? scy : scz)));
-            n0 = rec[0];
-            n1 = rec[1];
-            nm = *reinterpret_cast<const uint4 *>(rec + 2);
-        }
-    };
-
     for (;;) {
-        // ================= (A) refill idle lanes from the global ray counter =================
+        // ================= (A) retire finished rays, refill idle lanes from the global ray counter ==========
+        if (active && !walking && pend0 == kNoSphere && pend1 == kNoSphere) {
+            if (ANY) a.out_lit[pi] = h.occluded ? 0 : 1;
+            else { a.out_t[pi] = h.best.t; a.out_body[pi] = h.best.body; }
+            active = false;
+        }
         const uint32_t idle = __ballot_sync(0xffffffffu, !active);
         if (idle == 0xffffffffu && exhausted) break;
         if (!exhausted && (__popc(idle) >= a.g_refill)) {
@@ -155,8 +144,7 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
                 active = true;
                 walking = false;
                 pend0 = pend1 = kNoSphere;
-                fresh = false;
-                ok = oe = 0;
+                chain = 0;
                 pi = phys_index(a, ri);
                 const Ray ray = load_ray(a.q, pi);
                 h.best.init();
@@ -209,9 +197,9 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
                         }
                     }
                 }
-                ogx = ((float)op.x - g.lo[0]) * g.inv_cell[0];
-                ogy = ((float)op.y - g.lo[1]) * g.inv_cell[1];
-                ogz = ((float)op.z - g.lo[2]) * g.inv_cell[2];
+                const float ogx = ((float)op.x - g.lo[0]) * g.inv_cell[0];
+                const float ogy = ((float)op.y - g.lo[1]) * g.inv_cell[1];
+                const float ogz = ((float)op.z - g.lo[2]) * g.inv_cell[2];
                 const float dgx = (float)ray.d.x * g.inv_cell[0], dgy = (float)ray.d.y * g.inv_cell[1],
                             dgz = (float)ray.d.z * g.inv_cell[2];
                 const bool walkable = fabs(D2 - 1.0) <= kGridUnitTol && (misses_box || (fabsf(ogx) <= kGridMaxCoord &&
@@ -227,7 +215,7 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
                             if (!cull_reject(cr, s.cull4[sp])) exact_sphere<ANY>(s, ray, sp, h, n_exact, nan_count);
                         }
                         // clip the ray to the grid box [0, dim]
-                        ix = 1.0f / dgx; iy = 1.0f / dgy; iz = 1.0f / dgz;
+                        const float ix = 1.0f / dgx, iy = 1.0f / dgy, iz = 1.0f / dgz;
                         const float dimx = (float)g.dim[0], dimy = (float)g.dim[1], dimz = (float)g.dim[2];
                         float t0x = (0.0f - ogx) * ix, t1x = (dimx - ogx) * ix;
                         float t0y = (0.0f - ogy) * iy, t1y = (dimy - ogy) * iy;
@@ -239,104 +227,87 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
                         const float tenter = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
                         const float texit = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
                         // slack: the box walls are padded away from every sphere, so grazing rays may go either way
-                        if (!misses_box && tenter <= texit * 1.000001f + 1e-6f && tenter <= h.bound() - t0f) {
-                            cx = min(max((int)floorf(ogx + tenter * dgx), 0), g.dim[0] - 1);
-                            cy = min(max((int)floorf(ogy + tenter * dgy), 0), g.dim[1] - 1);
-                            cz = min(max((int)floorf(ogz + tenter * dgz), 0), g.dim[2] - 1);
-                            sxf = dgx > 0.0f ? 1.0f : (dgx < 0.0f ? -1.0f : 0.0f);
-                            syf = dgy > 0.0f ? 1.0f : (dgy < 0.0f ? -1.0f : 0.0f);
-                            szf = dgz > 0.0f ? 1.0f : (dgz < 0.0f ? -1.0f : 0.0f);
-                            // exit boundary of the start cell per axis; the parameter there is recomputed from the
-                            // boundary coordinate at every step (never accumulated)
-                            fbx = (float)(cx + (sxf > 0.0f));
-                            fby = (float)(cy + (syf > 0.0f));
-                            fbz = (float)(cz + (szf > 0.0f));
-                            tnx = sxf != 0.0f ? (fbx - ogx) * ix : kFltBig;
-                            tny = syf != 0.0f ? (fby - ogy) * iy : kFltBig;
-                            tnz = szf != 0.0f ? (fbz - ogz) * iz : kFltBig;
+                        boundf = h.bound() - t0f;
+                        if (!misses_box && tenter <= texit * 1.000001f + 1e-6f && tenter <= boundf) {
+                            const int cx = min(max((int)floorf(ogx + tenter * dgx), 0), g.dim[0] - 1);
+                            const int cy = min(max((int)floorf(ogy + tenter * dgy), 0), g.dim[1] - 1);
+                            const int cz = min(max((int)floorf(ogz + tenter * dgz), 0), g.dim[2] - 1);
+                            // per axis: exit plane of the grid (dim when stepping up, 0 when stepping down), the
+                            // parameter there, the parameter step per cell, and minus the boundaries before it.
+                            // An axis the ray does not move along never steps: tn = +big.
+                            tex = dgx > 0.0f ? (dimx - ogx) * ix : (dgx < 0.0f ? (0.0f - ogx) * ix : kFltBig);
+                            tey = dgy > 0.0f ? (dimy - ogy) * iy : (dgy < 0.0f ? (0.0f - ogy) * iy : kFltBig);
+                            tez = dgz > 0.0f ? (dimz - ogz) * iz : (dgz < 0.0f ? (0.0f - ogz) * iz : kFltBig);
+                            dtx = dgx != 0.0f ? fabsf(ix) : 0.0f;
+                            dty = dgy != 0.0f ? fabsf(iy) : 0.0f;
+                            dtz = dgz != 0.0f ? fabsf(iz) : 0.0f;
+                            kx = dgx > 0.0f ? (float)(cx + 1 - g.dim[0]) : (float)(-cx);
+                            ky = dgy > 0.0f ? (float)(cy + 1 - g.dim[1]) : (float)(-cy);
+                            kz = dgz > 0.0f ? (float)(cz + 1 - g.dim[2]) : (float)(-cz);
+                            tnx = fmaf(kx, dtx, tex);
+                            tny = fmaf(ky, dty, tey);
+                            tnz = fmaf(kz, dtz, tez);
                             cell = (cz * g.dim[1] + cy) * g.dim[0] + cx;
-                            scx = (int)sxf; scy = (int)syf * g.dim[0]; scz = (int)szf * g.dim[0] * g.dim[1];
+                            scx = dgx > 0.0f ? 1 : -1;
+                            scy = dgy > 0.0f ? g.dim[0] : -g.dim[0];
+                            scz = dgz > 0.0f ? g.dim[0] * g.dim[1] : -(g.dim[0] * g.dim[1]);
+                            tcur = tenter;
                             walking = true;
-                            fresh = true;
-                            {
-                                const float4 *rec = g.cell_rec + 3 * (size_t)cell;
-                                c0 = rec[0];
-                                c1 = rec[1];
-                                cm = *reinterpret_cast<const uint4 *>(rec + 2);
-                            }
-                            prefetch_next();
                         }
                     }
                 }
             }
         }
 
-        // ================= (B) scan: one cell per step — fetch its record, cull its two inline items ====
+        // ================= (B) scan: one 48-byte record per step ======================================
+        // A scanning lane fetches ONE record per step and culls its two items: either the first record of
+        // the next cell of its walk — the DDA then advances to the cell after it WHILE the fetch is in flight
+        // (the step does not depend on what the cell holds) — or the next chained record of the cell it is
+        // in (cells with more than two items).  Both cases run the same instruction stream (the step is
+        // predicated), so a warp never serialises a rare per-lane path.  Records live only inside one
+        // iteration: nothing of them stays in registers across the refill and exact-test phases.
 #pragma unroll 1
         for (int burst = 0; burst < a.g_burst; ++burst) {
-            const bool go = active && pend0 == kNoSphere && pend1 == kNoSphere;
+            bool go = active && walking && pend0 == kNoSphere && pend1 == kNoSphere;
+            const bool enter = chain == 0u;   // the next record is a new cell's first
+            if (go && enter && ((ANY && h.occluded) || boundf < fmaf(tcur, 0.99999f, -1e-5f))) {
+                walking = false;   // nothing nearer can lie in or beyond this cell (or the walk has left the grid)
+                go = false;
+            }
             if (STATS) {
-                st_lane_steps += (go && walking) ? 1u : 0u;
+                st_lane_steps += go ? 1u : 0u;
                 if (lane == 0) st_lane_slots += 32u;
             }
-            if (go && walking) {
-                if (fresh) {
-                    if (STATS) { ++st_cells; st_fetch += (cm.x != kNoSphere) ? 1u : 0u; st_culls += (cm.x != kNoSphere) + (cm.y != kNoSphere); }
-                    // examine the current cell: its two inline items now, an overflow list (cells with
-                    // more than two items, a few per cent) two items per step below
-                    if (cm.x != kNoSphere && !cull_reject(cr, c0)) pend0 = cm.x;
-                    if (cm.y != kNoSphere && !cull_reject(cr, c1)) pend1 = cm.y;
-                    ok = cm.z;
-                    oe = cm.w;
-                    fresh = false;
-                } else if (ok < oe) {
-                    if (STATS) st_culls += (ok + 1 < oe) ? 2u : 1u;
-                    if (!cull_reject(cr, g.cell_cull4[ok])) pend0 = g.cell_items[ok];
-                    if (ok + 1 < oe && !cull_reject(cr, g.cell_cull4[ok + 1])) pend1 = g.cell_items[ok + 1];
-                    ok += 2;
-                }
-                if (pend0 == kNoSphere && pend1 == kNoSphere && ok >= oe) {
-                    // every item of the current cell is decided: stop, or step to the next cell
-                    // (branch-free axis choice; its record was prefetched)
+            if (go) {
+                const float4 *rec = g.cell_rec + 3 * (size_t)(enter ? (uint32_t)cell : chain);
+                const float4 c0 = rec[0], c1 = rec[1];
+                const uint4 cm = *reinterpret_cast<const uint4 *>(rec + 2);
+                if (enter) {
+                    // step: the axis whose boundary comes first; tn = tex + k * dt recomputed, never accumulated
                     const float tnext = fminf(tnx, fminf(tny, tnz));
-                    bool stop = (ANY && h.occluded) || (h.bound() - t0f < tnext * 0.99999f - 1e-5f);
                     const bool ax = tnx <= tny && tnx <= tnz;
                     const bool ay = !ax && tny <= tnz;
                     const bool az = !ax && !ay;
-                    cx += ax ? (int)sxf : 0; cy += ay ? (int)syf : 0; cz += az ? (int)szf : 0;
-                    fbx += ax ? sxf : 0.0f; fby += ay ? syf : 0.0f; fbz += az ? szf : 0.0f;
-                    tnx = ax ? (fbx - ogx) * ix : tnx;
-                    tny = ay ? (fby - ogy) * iy : tny;
-                    tnz = az ? (fbz - ogz) * iz : tnz;
+                    kx += ax ? 1.0f : 0.0f;
+                    ky += ay ? 1.0f : 0.0f;
+                    kz += az ? 1.0f : 0.0f;
+                    tnx = fmaf(kx, dtx, tex);
+                    tny = fmaf(ky, dty, tey);
+                    tnz = fmaf(kz, dtz, tez);
                     cell += ax ? scx : (ay ? scy : scz);
-                    stop = stop || (unsigned)cx >= (unsigned)g.dim[0] || (unsigned)cy >= (unsigned)g.dim[1] ||
-                           (unsigned)cz >= (unsigned)g.dim[2];
-                    walking = !stop;
-                    if (walking) {
-                        if (kGridPrefetch) { c0 = n0; c1 = n1; cm = nm; }
-                        else {
-                            const float4 *rec = g.cell_rec + 3 * (size_t)cell;
-                            c0 = rec[0];
-                            c1 = rec[1];
-                            cm = *reinterpret_cast<const uint4 *>(rec + 2);
-                        }
-                        fresh = true;
-                        prefetch_next();
-                    }
+                    tcur = fmaxf(kx, fmaxf(ky, kz)) > 0.0f ? kFltInf : tnext;   // k > 0: that boundary was the grid's exit plane (+inf beats every bound)
                 }
-            }
-            if (go && !walking && pend0 == kNoSphere && pend1 == kNoSphere) {
-                // ---- finished: write the result, free the lane
-                if (ANY) a.out_lit[pi] = h.occluded ? 0 : 1;
-                else { a.out_t[pi] = h.best.t; a.out_body[pi] = h.best.body; }
-                active = false;
+                if (STATS) { st_cells += enter ? 1u : 0u; st_fetch += (cm.x != kNoSphere) ? 1u : 0u; st_culls += (cm.x != kNoSphere) + (cm.y != kNoSphere); }
+                if (cm.x != kNoSphere && !cull_reject(cr, c0)) pend0 = cm.x;
+                if (cm.y != kNoSphere && !cull_reject(cr, c1)) pend1 = cm.y;
+                chain = cm.z;
             }
         }
 
         // ================= (C) exact tests of the parked candidates, many lanes at a time ==========
         const bool has_pending = pend0 != kNoSphere || pend1 != kNoSphere;
         const uint32_t waiting = __ballot_sync(0xffffffffu, has_pending);
-        const uint32_t scanning = __ballot_sync(0xffffffffu, active && !has_pending);
+        const uint32_t scanning = __ballot_sync(0xffffffffu, active && walking && !has_pending);
         if (waiting && (__popc(waiting) >= a.g_quorum || scanning == 0u ||
                         (exhausted && __popc(waiting) * 2 >= __popc(waiting | scanning)))) {
             if (has_pending) {
@@ -344,6 +315,7 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
                 if (pend0 != kNoSphere) exact_sphere<ANY>(s, ray, pend0, h, n_exact, nan_count);
                 if (pend1 != kNoSphere) exact_sphere<ANY>(s, ray, pend1, h, n_exact, nan_count);
                 pend0 = pend1 = kNoSphere;
+                boundf = h.bound() - t0f;
             }
         }
     }

@@ -53,7 +53,8 @@ struct GridDev {            // see rg_grid.cuh
     const uint32_t *cell_start;   // [ncells + 1]
     const uint32_t *cell_items;   // sphere indices (into the sphere list), cell by cell
     const float4 *cell_cull4;     // the same spheres' FP32 cull records, in the same order
-    const float4 *cell_rec;       // [ncells][3]: cull record of item 0, of item 1, (idx0, idx1, overflow begin, end)
+    const float4 *cell_rec;       // [nrecords][3]: cull record of item 0, of item 1, (idx0, idx1, next record of the cell | 0, -);
+                                  // records [0, ncells) are the cells' first, chained ones follow (rg_grid.cuh)
     uint32_t n_loose;             // spheres kept out of the grid (too large): brute-forced
     const uint32_t *loose;        // their sphere-list indices
     uint32_t enabled;

@@ -27,6 +27,36 @@ namespace rg {
 constexpr uint32_t kChildDefault = 0xFFFFFFFFu;   // child colour is scene.default_color (no node)
 enum : uint32_t { NODE_MISS = 0, NODE_DIFFUSE = 1, NODE_REFLECTING = 2, NODE_REFRACTIVE = 3 };
 
+// ---- ray reordering between levels -------------------------------------------------------------
+// Primary rays are coherent (one origin, smoothly varying directions); their children are not: after
+// one or two bounces neighbouring queue entries start anywhere and go anywhere, every lane of a warp
+// walks different cells and the trace kernels run ~3x slower per ray (measured: a shuffled level-0
+// queue costs what every deeper level costs).  So the children of a level are binned before they are
+// traced: bin = (coarse grid region of the origin, direction octant), one counting sort per level
+// (histogram in k_shade, scan, scatter).  The scatter also patches the parent's child link, so nodes,
+// hits, shadow rays and grandchildren all inherit the new order.  Results do not depend on queue order.
+constexpr uint32_t kMaxBins = 8192;
+struct BinParams {
+    uint32_t enabled;
+    uint32_t shift;          // coarse region = grid cell >> shift
+    uint32_t nx, ny, nz;     // coarse regions per axis
+    uint32_t nbins;          // nx * ny * nz * 8 <= kMaxBins
+};
+
+__device__ __forceinline__ uint32_t ray_bin(const DScene &s, const BinParams &b, const Ray &r) {
+    const GridDev &g = s.grid;
+    const float gx = ((float)(r.o.x - s.cull_ref[0]) - g.lo[0]) * g.inv_cell[0];
+    const float gy = ((float)(r.o.y - s.cull_ref[1]) - g.lo[1]) * g.inv_cell[1];
+    const float gz = ((float)(r.o.z - s.cull_ref[2]) - g.lo[2]) * g.inv_cell[2];
+    // clamp in float first (NaN -> 0 through fmaxf/fminf, far-away origins -> a border region)
+    const uint32_t cx = (uint32_t)fminf(fmaxf(gx, 0.0f), (float)(g.dim[0] - 1)) >> b.shift;
+    const uint32_t cy = (uint32_t)fminf(fmaxf(gy, 0.0f), (float)(g.dim[1] - 1)) >> b.shift;
+    const uint32_t cz = (uint32_t)fminf(fmaxf(gz, 0.0f), (float)(g.dim[2] - 1)) >> b.shift;
+    const uint32_t oct = (r.d.x < 0.0 ? 1u : 0u) | (r.d.y < 0.0 ? 2u : 0u) | (r.d.z < 0.0 ? 4u : 0u);
+    const uint32_t key = ((cz * b.ny + cy) * b.nx + cx) * 8u + oct;
+    return key < b.nbins ? key : b.nbins - 1u;
+}
+
 struct LevelBuffers {
     RayQueue cur, next, shadow;
     const double *hit_t;
@@ -47,6 +77,11 @@ struct LevelBuffers {
     unsigned int *void_flag;         // set when a queue overflows; once set, every later launch does nothing
     uint32_t level;                  // recursion depth of this level
     uint32_t count_on_device;        // shadow rays / deepest level are counted in DCounters (host-free loop)
+    // ray reordering (see k_bin_scatter): `next` is then a staging queue, and per child k_shade also leaves
+    uint32_t *next_key;              // ... its bin,
+    uint32_t *next_meta;             // ... its parent node (bit 31: it is the transmission child),
+    unsigned int *bin_count;         // ... and a histogram of the bins
+    BinParams bins;
 };
 
 // Size of a level as its kernels see it (host-sized, or read from the device and clamped to the capacity).
@@ -57,15 +92,41 @@ __device__ __forceinline__ uint32_t level_size(uint32_t n, const unsigned int *n
     return v < n ? v : n;
 }
 
+// Order of the level-0 queue.  Rows of a batch are taken in strips of `strip` rows and a strip is
+// walked column by column, so 32 consecutive rays (a warp of every later kernel) cover a compact
+// (32 / strip) x strip tile of the image instead of a 32 x 1 run: neighbouring lanes hit the same
+// body, their shadow rays and children stay together, and the whole ray tree below inherits the
+// locality (queues are compacted in parent order).  Pure index permutation: results are unchanged.
+struct PixelOrder {
+    uint32_t width, rows, strip;   // batch geometry
+    uint32_t mul, inv, npix;       // experiment (RG_SHUFFLE_PIXELS): i -> i * mul mod npix destroys all coherence
+    // queue index -> (x, batch row)
+    __device__ __forceinline__ void pixel(uint32_t i, uint32_t &x, uint32_t &r) const {
+        if (mul) i = (uint32_t)(((uint64_t)i * mul) % npix);
+        const uint32_t per = strip * width, sidx = i / per, j = i - sidx * per;
+        const uint32_t hs = min(strip, rows - sidx * strip);
+        x = j / hs;
+        r = sidx * strip + (j - x * hs);
+    }
+    // (x, batch row) -> queue index
+    __device__ __forceinline__ uint32_t index(uint32_t x, uint32_t r) const {
+        const uint32_t sidx = r / strip, hs = min(strip, rows - sidx * strip);
+        const uint32_t i = sidx * strip * width + x * hs + (r - sidx * strip);
+        return mul ? (uint32_t)(((uint64_t)i * inv) % npix) : i;
+    }
+};
+
 // rendering.rs:71-72 + ray.rs:37-54: the level-0 queue, one ray per pixel of rows [y0, y1)
 // `rows` (optional) maps the k-th row of the batch to an image row, for row-tile sharding.
 __global__ void __launch_bounds__(256) k_generate(const DScene s, RayQueue q, uint32_t width, uint32_t height,
                                                   uint32_t y0, uint32_t npix, const uint32_t *__restrict__ rows,
-                                                  unsigned int *n_level0) {
+                                                  unsigned int *n_level0, const PixelOrder po) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && n_level0) *n_level0 = npix;
     if (i >= npix) return;
-    const uint32_t k = y0 + i / width, x = i % width;
+    uint32_t x, r;
+    po.pixel(i, x, r);
+    const uint32_t k = y0 + r;
     const uint32_t y = rows ? rows[k] : k;
     store_ray(q, i, create_prime(s, x, y, width, height));
 }
@@ -157,10 +218,22 @@ __global__ void __launch_bounds__(256) k_shade(const DScene s, const LevelBuffer
     if (want_refl) {
         child_refl = base_next + __popc(m_refl & lt);
         store_ray(lb.next, child_refl, refl);
+        if (lb.bins.enabled) {
+            const uint32_t key = ray_bin(s, lb.bins, refl);
+            lb.next_key[child_refl] = key;
+            lb.next_meta[child_refl] = i;
+            atomicAdd(&lb.bin_count[key], 1u);
+        }
     }
     if (want_trans) {
         child_trans = base_next + __popc(m_refl) + __popc(m_trans & lt);
         store_ray(lb.next, child_trans, trans);
+        if (lb.bins.enabled) {
+            const uint32_t key = ray_bin(s, lb.bins, trans);
+            lb.next_key[child_trans] = key;
+            lb.next_meta[child_trans] = i | 0x80000000u;
+            atomicAdd(&lb.bin_count[key], 1u);
+        }
     }
     if (want_lit) {
         // shade_diffuse's per-light setup (rendering.rs:141-149,163): shadow ray from
@@ -237,45 +310,99 @@ __global__ void __launch_bounds__(256) k_combine(const DScene s, float4 *node_a,
     }
 }
 
+// exclusive prefix sum of the bin histogram (<= kMaxBins entries): one 1024-thread block
+__global__ void __launch_bounds__(1024) k_bin_scan(const unsigned int *__restrict__ count, unsigned int *base, uint32_t nbins) {
+    __shared__ uint32_t part[1024];
+    const uint32_t t = threadIdx.x, per = (nbins + 1023u) / 1024u;
+    const uint32_t lo = min(nbins, t * per), hi = min(nbins, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t k = lo; k < hi; ++k) sum += count[k];
+    part[t] = sum;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024u; off <<= 1) {
+        const uint32_t v = t >= off ? part[t - off] : 0u;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = t ? part[t - 1] : 0u;
+    for (uint32_t k = lo; k < hi; ++k) { base[k] = run; run += count[k]; }
+}
+
+// moves every staged child to its place in the binned queue and tells its parent where it went
+__global__ void __launch_bounds__(256) k_bin_scatter(const RayQueue staged, const RayQueue sorted, const uint32_t *__restrict__ key,
+                                                     const uint32_t *__restrict__ meta, const unsigned int *__restrict__ base,
+                                                     unsigned int *cursor, uint4 *parent_b, uint32_t cap,
+                                                     const unsigned int *n_dev, const unsigned int *void_flag) {
+    const uint32_t n = level_size(cap, n_dev, void_flag);
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {
+        const uint32_t i = i0 + lane;
+        const bool have = i < n;
+        const uint32_t k = have ? key[i] : 0xFFFFFFFFu;
+        // one atomic per distinct bin of the warp (neighbours mostly share a bin)
+        const uint32_t peers = __match_any_sync(0xffffffffu, k);
+        const uint32_t leader = __ffs(peers) - 1u;
+        uint32_t first = 0;
+        if (have && lane == leader) first = atomicAdd(&cursor[k], (unsigned)__popc(peers));
+        first = __shfl_sync(0xffffffffu, first, leader);
+        if (have) {
+            const uint32_t pos = base[k] + first + __popc(peers & ((1u << lane) - 1u));
+            const double2 a = staged.a[i], b = staged.b[i], c = staged.c[i];
+            sorted.a[pos] = a; sorted.b[pos] = b; sorted.c[pos] = c;
+            const uint32_t m = meta[i];
+            uint32_t *link = reinterpret_cast<uint32_t *>(parent_b + (m & 0x7FFFFFFFu));
+            link[m >> 31] = pos;   // .x = reflection child, .y = transmission child
+        }
+    }
+}
+
 __device__ __forceinline__ uint32_t pack_rgba(uchar4 c) {
     return (uint32_t)c.x | ((uint32_t)c.y << 8) | ((uint32_t)c.z << 16) | ((uint32_t)c.w << 24);
 }
 
-// Color::rgba (color.rs:32-37): 4 pixels per thread, one 128-bit store
-__global__ void __launch_bounds__(256) k_quantise(const float4 *__restrict__ node_a, uchar4 *out, uint32_t npix) {
-    const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
-    if (i4 >= npix) return;
-    if (i4 + 4u <= npix && (reinterpret_cast<uintptr_t>(out + i4) & 15u) == 0) {
+// Color::rgba (color.rs:32-37): 4 pixels of a row per thread, one 128-bit store; the level-0 nodes are
+// gathered through the queue order (PixelOrder).
+__global__ void __launch_bounds__(256) k_quantise(const float4 *__restrict__ node_a, uchar4 *out, uint32_t npix, const PixelOrder po) {
+    const uint32_t p4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;   // first of 4 pixels, row-major in the batch
+    if (p4 >= npix) return;
+    const uint32_t r = p4 / po.width, x = p4 - r * po.width;
+    if (x + 4u <= po.width && (reinterpret_cast<uintptr_t>(out + p4) & 15u) == 0) {
         uint32_t p[4];   // one packed RGBA8 word per pixel, stored as one 128-bit word
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { float4 a = node_a[i4 + k]; p[k] = pack_rgba(quantise(c3(a.x, a.y, a.z))); }
-        *reinterpret_cast<uint4 *>(out + i4) = make_uint4(p[0], p[1], p[2], p[3]);
+        for (uint32_t k = 0; k < 4; ++k) { float4 a = node_a[po.index(x + k, r)]; p[k] = pack_rgba(quantise(c3(a.x, a.y, a.z))); }
+        *reinterpret_cast<uint4 *>(out + p4) = make_uint4(p[0], p[1], p[2], p[3]);
     } else {
-        for (uint32_t k = i4; k < npix && k < i4 + 4u; ++k) { float4 a = node_a[k]; out[k] = quantise(c3(a.x, a.y, a.z)); }
+        for (uint32_t k = p4; k < npix && k < p4 + 4u; ++k) {
+            const uint32_t rk = k / po.width;
+            float4 a = node_a[po.index(k - rk * po.width, rk)];
+            out[k] = quantise(c3(a.x, a.y, a.z));
+        }
     }
 }
 
-// The same, fused with the gather of a sharded frame: pixel i of the batch belongs to image row
-// rows[row0 + i / width] and is stored at its place in a FULL frame that may live in another
-// GPU's memory (a CUDA-IPC mapping written over NVLink): the "collective" of this path is these
-// stores, and nothing is left to exchange when the kernel retires.
+// The same, fused with the gather of a sharded frame: batch row r belongs to image row
+// rows[row0 + r] and is stored at its place in a FULL frame that may live in another
+// GPU's memory (a CUDA-IPC mapping written over NVLink) or in pinned host memory: the "collective"
+// of this path is these stores, and nothing is left to exchange when the kernel retires.
 __global__ void __launch_bounds__(256) k_quantise_scatter(const float4 *__restrict__ node_a, uchar4 *frame, uint32_t npix,
-                                                          uint32_t width, const uint32_t *__restrict__ rows, uint32_t row0) {
-    const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
-    if (i4 >= npix) return;
-    const uint32_t r = i4 / width, x = i4 - r * width;
-    if (x + 4u <= width && i4 + 4u <= npix) {
+                                                          const uint32_t *__restrict__ rows, uint32_t row0, const PixelOrder po) {
+    const uint32_t p4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (p4 >= npix) return;
+    const uint32_t width = po.width;
+    const uint32_t r = p4 / width, x = p4 - r * width;
+    if (x + 4u <= width) {
         uchar4 *dst = frame + (size_t)rows[row0 + r] * width + x;
         uint32_t p[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { float4 a = node_a[i4 + k]; p[k] = pack_rgba(quantise(c3(a.x, a.y, a.z))); }
+        for (uint32_t k = 0; k < 4; ++k) { float4 a = node_a[po.index(x + k, r)]; p[k] = pack_rgba(quantise(c3(a.x, a.y, a.z))); }
         if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) *reinterpret_cast<uint4 *>(dst) = make_uint4(p[0], p[1], p[2], p[3]);
         else { uint32_t *d32 = reinterpret_cast<uint32_t *>(dst); d32[0] = p[0]; d32[1] = p[1]; d32[2] = p[2]; d32[3] = p[3]; }
     } else {
-        for (uint32_t k = i4; k < npix && k < i4 + 4u; ++k) {
-            const uint32_t rk = k / width;
-            float4 a = node_a[k];
-            frame[(size_t)rows[row0 + rk] * width + (k - rk * width)] = quantise(c3(a.x, a.y, a.z));
+        for (uint32_t k = p4; k < npix && k < p4 + 4u; ++k) {
+            const uint32_t rk = k / width, xk = k - rk * width;
+            float4 a = node_a[po.index(xk, rk)];
+            frame[(size_t)rows[row0 + rk] * width + xk] = quantise(c3(a.x, a.y, a.z));
         }
     }
 }
@@ -309,6 +436,29 @@ __global__ void __launch_bounds__(128) k_verify_trace(const DScene s, const Trac
 static bool shadow_light_major() {
     static const bool v = [] { const char *e = getenv("RG_SHADOW_LIGHT_MAJOR"); return e && atoi(e) != 0; }();
     return v;
+}
+
+// strip height of the level-0 queue order (RG_STRIP_ROWS for tuning; 1 = plain row-major)
+static PixelOrder pixel_order(uint32_t width, uint32_t rows) {
+    static const uint32_t strip = [] { const char *e = getenv("RG_STRIP_ROWS"); const int v = e ? atoi(e) : 4; return (uint32_t)(v >= 1 && v <= 32 ? v : 4); }();
+    PixelOrder po;
+    po.width = width;
+    po.rows = rows;
+    po.strip = strip;
+    po.mul = po.inv = 0;
+    po.npix = width * rows;
+    static const bool shuffle = [] { const char *e = getenv("RG_SHUFFLE_PIXELS"); return e && atoi(e) != 0; }();
+    if (shuffle && po.npix > 2) {   // a multiplier coprime to npix and its modular inverse (extended Euclid)
+        uint64_t m = 2654435761ull % po.npix;
+        auto gcd = [](uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; };
+        while (m < 2 || gcd(m, po.npix) != 1) ++m;
+        long long t = 0, nt = 1, r = po.npix, nr = (long long)m;
+        while (nr) { long long q = r / nr, tt = t - q * nt; t = nt; nt = tt; long long rr = r - q * nr; r = nr; nr = rr; }
+        if (t < 0) t += po.npix;
+        po.mul = (uint32_t)m;
+        po.inv = (uint32_t)t;
+    }
+    return po;
 }
 
 static RayQueue make_queue(DeviceBuffer &b, size_t cap) {
@@ -467,7 +617,8 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
     uint32_t n = npix, d = 0;
     if ((rc = wf.ray[0].reserve((size_t)n * 48))) return rc;
     RayQueue cur = make_queue(wf.ray[0], n);
-    k_generate<<<blocks(n), 256, 0, stream>>>(ds, cur, width, height, y0, npix, d_rows, nullptr);
+    const PixelOrder po = pixel_order(width, y1 - y0);
+    k_generate<<<blocks(n), 256, 0, stream>>>(ds, cur, width, height, y0, npix, d_rows, nullptr, po);
     RG_CUDA(cudaGetLastError());
     st->gpu_launches++;
     st->rays_primary += npix;
@@ -619,9 +770,9 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
         st->gpu_launches++;
     }
     if (sc->scatter_out)   // d_out is the base of the whole frame; this batch covers row-list entries [y0, y1)
-        k_quantise_scatter<<<blocks(((uint64_t)npix + 3) / 4), 256, 0, stream>>>(wf.nodes[0].as<float4>(), d_out, npix, width, d_rows, y0);
+        k_quantise_scatter<<<blocks(((uint64_t)npix + 3) / 4), 256, 0, stream>>>(wf.nodes[0].as<float4>(), d_out, npix, d_rows, y0, po);
     else
-        k_quantise<<<blocks(((uint64_t)npix + 3) / 4), 256, 0, stream>>>(wf.nodes[0].as<float4>(), d_out, npix);
+        k_quantise<<<blocks(((uint64_t)npix + 3) / 4), 256, 0, stream>>>(wf.nodes[0].as<float4>(), d_out, npix, po);
     RG_CUDA(cudaGetLastError());
     st->gpu_launches++;
     st->batches++;
@@ -646,9 +797,29 @@ constexpr uint32_t kLevelGrowth = 2;
 struct DevPlan {
     uint32_t levels = 0;                    // levels 0 .. levels-1 are enqueued
     uint32_t cap[RG_MAX_DEPTH + 2] = {0};
+    BinParams bins{};                       // ray reordering between levels (grid tracer only)
 };
 
-static int plan_batch_dev(rg_scene *sc, uint32_t npix, DevPlan &plan) {
+// RG_OPT_REORDER: 0 = automatic (on with the grid tracer), 1 = off, 2 = on
+static BinParams bin_params(const rg_scene *sc, bool use_grid) {
+    BinParams b{};
+    static const int env = [] { const char *e = getenv("RG_REORDER"); return e ? atoi(e) : -1; }();
+    const int mode = env >= 0 ? env : sc->reorder;
+    const GridDev &g = sc->ds.grid;
+    if (mode != 2 || !use_grid || !g.enabled) return b;   // measured: bins of this coarseness buy ~6 % on the traces and cost more than that
+    static const uint32_t max_regions = [] { const char *e = getenv("RG_REORDER_REGIONS"); const int v = e ? atoi(e) : 0; return (uint32_t)(v > 0 ? v : (int)(kMaxBins / 8)); }();
+    for (uint32_t shift = 0; shift < 9; ++shift) {
+        const uint32_t nx = ((uint32_t)g.dim[0] + (1u << shift) - 1) >> shift, ny = ((uint32_t)g.dim[1] + (1u << shift) - 1) >> shift,
+                       nz = ((uint32_t)g.dim[2] + (1u << shift) - 1) >> shift;
+        if ((uint64_t)nx * ny * nz <= std::min<uint32_t>(max_regions, kMaxBins / 8)) {
+            b.enabled = 1; b.shift = shift; b.nx = nx; b.ny = ny; b.nz = nz; b.nbins = nx * ny * nz * 8u;
+            break;
+        }
+    }
+    return b;
+}
+
+static int plan_batch_dev(rg_scene *sc, uint32_t npix, DevPlan &plan, bool use_grid) {
     const DScene &ds = sc->ds;
     const uint32_t L = ds.n_lights;
     WavefrontScratch &wf = sc->wf;
@@ -680,6 +851,14 @@ static int plan_batch_dev(rg_scene *sc, uint32_t npix, DevPlan &plan) {
         if ((rc = wf.lit_bc[p].reserve((size_t)c * 16))) return rc;
         if ((rc = wf.lit_node[p].reserve((size_t)c * 4))) return rc;
     }
+    plan.bins = bin_params(sc, use_grid);
+    if (plan.bins.enabled && plan.levels > 1) {
+        const uint64_t c = std::max<uint64_t>(std::max(cap_max[0], cap_max[1]), 1);
+        if ((rc = wf.stage_ray.reserve((size_t)c * 48))) return rc;
+        if ((rc = wf.stage_key.reserve((size_t)c * 4))) return rc;
+        if ((rc = wf.stage_meta.reserve((size_t)c * 4))) return rc;
+        if ((rc = wf.bins.reserve((size_t)plan.levels * 3 * kMaxBins * sizeof(unsigned int)))) return rc;
+    }
     return RG_OK;
 }
 
@@ -702,8 +881,11 @@ static int enqueue_batch_dev(rg_scene *sc, const DevPlan &plan, uint32_t width, 
     cudaEvent_t shadow_done[2] = {nullptr, nullptr};
 
     RG_CUDA(cudaMemsetAsync(dc->lvl, 0, sizeof(dc->lvl), stream));
+    const bool reorder = plan.bins.enabled && plan.levels > 1;
+    if (reorder) RG_CUDA(cudaMemsetAsync(wf.bins.ptr, 0, (size_t)plan.levels * 3 * kMaxBins * sizeof(unsigned int), stream));
     RayQueue cur = make_queue(wf.ray[0], plan.cap[0]);
-    k_generate<<<(npix + 255) / 256, 256, 0, stream>>>(ds, cur, width, height, y0, npix, d_rows, &dc->lvl[0].n);
+    const PixelOrder po = pixel_order(width, npix / width);
+    k_generate<<<(npix + 255) / 256, 256, 0, stream>>>(ds, cur, width, height, y0, npix, d_rows, &dc->lvl[0].n, po);
     RG_CUDA(cudaGetLastError());
     st->gpu_launches++;
     st->rays_primary += npix;
@@ -752,10 +934,31 @@ static int enqueue_batch_dev(rg_scene *sc, const DevPlan &plan, uint32_t width, 
         lb.void_flag = &dc->overflow;
         lb.level = d;
         lb.count_on_device = 1u;
+        const RayQueue next_sorted = lb.next;
+        unsigned int *bin_count = nullptr, *bin_base = nullptr, *bin_cursor = nullptr;
+        const bool bin_this = reorder && can_spawn;
+        if (bin_this) {   // children are staged, then moved to their bins (k_bin_scatter)
+            bin_count = wf.bins.as<unsigned int>() + (size_t)d * 3 * kMaxBins;
+            bin_base = bin_count + kMaxBins;
+            bin_cursor = bin_base + kMaxBins;
+            lb.next = make_queue(wf.stage_ray, std::max<uint32_t>(cap_next, 1u));
+            lb.next_key = wf.stage_key.as<uint32_t>();
+            lb.next_meta = wf.stage_meta.as<uint32_t>();
+            lb.bin_count = bin_count;
+            lb.bins = plan.bins;
+        }
         if (shadow_done[p]) RG_CUDA(cudaStreamWaitEvent(stream, shadow_done[p], 0));   // level d-2 still reads these buffers
         k_shade<<<blocks(cap), 256, 0, stream>>>(ds, lb, dc);
         RG_CUDA(cudaGetLastError());
         st->gpu_launches++;
+        if (bin_this) {
+            k_bin_scan<<<1, 1024, 0, stream>>>(bin_count, bin_base, plan.bins.nbins);
+            k_bin_scatter<<<blocks(cap_next), 256, 0, stream>>>(lb.next, next_sorted, lb.next_key, lb.next_meta, bin_base, bin_cursor,
+                                                              lb.node_b, cap_next, &dc->lvl[d + 1].n, &dc->overflow);
+            RG_CUDA(cudaGetLastError());
+            st->gpu_launches += 2;
+            lb.next = next_sorted;
+        }
 
         if (L) {   // shadow side, concurrent with the next level's path side
             if (overlap) {
@@ -800,9 +1003,9 @@ static int enqueue_batch_dev(rg_scene *sc, const DevPlan &plan, uint32_t width, 
         st->gpu_launches++;
     }
     if (sc->scatter_out)
-        k_quantise_scatter<<<(unsigned)((((uint64_t)npix + 3) / 4 + 255) / 256), 256, 0, stream>>>(wf.nodes[0].as<float4>(), d_out, npix, width, d_rows, y0);
+        k_quantise_scatter<<<(unsigned)((((uint64_t)npix + 3) / 4 + 255) / 256), 256, 0, stream>>>(wf.nodes[0].as<float4>(), d_out, npix, d_rows, y0, po);
     else
-        k_quantise<<<(unsigned)((((uint64_t)npix + 3) / 4 + 255) / 256), 256, 0, stream>>>(wf.nodes[0].as<float4>(), d_out, npix);
+        k_quantise<<<(unsigned)((((uint64_t)npix + 3) / 4 + 255) / 256), 256, 0, stream>>>(wf.nodes[0].as<float4>(), d_out, npix, po);
     RG_CUDA(cudaGetLastError());
     st->gpu_launches++;
     st->batches++;
@@ -815,9 +1018,9 @@ static std::vector<uint64_t> graph_key(const rg_scene *sc, const DevPlan &plan, 
     const WavefrontScratch &wf = sc->wf;
     std::vector<uint64_t> k = {width, height, y0, npix, (uint64_t)(uintptr_t)d_rows, (uint64_t)(uintptr_t)d_out,
                                (uint64_t)use_grid, (uint64_t)sc->scatter_out, (uint64_t)sc->ds.max_depth, (uint64_t)sc->overlap,
-                               (uint64_t)sc->verify_cull, (uint64_t)sc->trace_stats, (uint64_t)plan.levels};
+                               (uint64_t)sc->verify_cull, (uint64_t)sc->trace_stats, (uint64_t)plan.levels, (uint64_t)plan.bins.nbins};
     auto add = [&](const DeviceBuffer &b) { k.push_back((uint64_t)(uintptr_t)b.ptr); };
-    add(wf.ray[0]); add(wf.ray[1]); add(wf.hit_t); add(wf.hit_body);
+    add(wf.ray[0]); add(wf.ray[1]); add(wf.hit_t); add(wf.hit_body); add(wf.stage_ray); add(wf.stage_key); add(wf.stage_meta); add(wf.bins);
     for (int p = 0; p < 2; ++p) { add(wf.sray[p]); add(wf.s_tmax[p]); add(wf.s_ab[p]); add(wf.s_lit[p]); add(wf.lit_bc[p]); add(wf.lit_node[p]); }
     for (uint32_t d = 0; d < plan.levels; ++d) add(wf.nodes[d]);
     return k;
@@ -920,7 +1123,7 @@ int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0,
                 DevPlan plan;
                 const uint64_t npix64 = (uint64_t)(ye - y) * width;
                 if (npix64 > 0x7FFFFFFFull) { set_error("batch of %llu pixels is too large", (unsigned long long)npix64); rc = RG_E_NOMEM; }
-                else if (npix64 && (rc = plan_batch_dev(sc, (uint32_t)npix64, plan)) == RG_OK) {
+                else if (npix64 && (rc = plan_batch_dev(sc, (uint32_t)npix64, plan, use_grid)) == RG_OK) {
                     bool done = false;
                     if (sc->graph != 1 && sc->verify_cull == 0)
                         rc = graph_batch(sc, plan, width, height, y, (uint32_t)npix64, d_rows, out, stream, st, use_grid, sync_events, &done);
