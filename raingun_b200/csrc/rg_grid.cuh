@@ -38,10 +38,10 @@ constexpr float kGridInflate = 2e-3f;       // in cells; see above
 constexpr float kGridMaxCoord = 2048.0f;    // |grid coordinate| limit for FP32 traversal
 constexpr double kGridUnitTol = 1e-9;
 constexpr int kGridRefill = 12;             // refill when at least this many lanes are idle
-constexpr int kGridExactQuorum = 10;        // evaluate pending candidates when this many lanes wait
+constexpr int kGridExactQuorum = 6;         // evaluate pending candidates when this many lanes wait
 constexpr int kGridScanBurst = 4;           // scan steps between quorum checks
 #ifndef RG_GRID_MINB
-#define RG_GRID_MINB 6
+#define RG_GRID_MINB 7   // CTAs per SM the register budget is set for (72 registers; measured 4..8)
 #endif
 constexpr uint32_t kNoSphere = 0xFFFFFFFFu;
 constexpr float kFltBig = 3.4e38f;
@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const uint32_t n_rays = ray_count(a);
+    const uint32_t seg_len = segment_length(a);
     unsigned n_exact = 0, nan_count = 0;
     unsigned long long st_cells = 0, st_fetch = 0, st_culls = 0, st_refills = 0, st_lane_steps = 0, st_lane_slots = 0;
 
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
                 walking = false;
                 pend0 = pend1 = kNoSphere;
                 chain = 0;
-                pi = phys_index(a, ri);
+                pi = phys_index(seg_len, a.seg_stride, ri);
                 const Ray ray = load_ray(a.q, pi);
                 h.best.init();
                 h.occluded = false;
@@ -311,9 +312,12 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
         if (waiting && (__popc(waiting) >= a.g_quorum || scanning == 0u ||
                         (exhausted && __popc(waiting) * 2 >= __popc(waiting | scanning)))) {
             if (has_pending) {
+                // every waiting lane runs the first test together; a second survivor of the same record is rare
                 const Ray ray = load_ray(a.q, pi);
-                if (pend0 != kNoSphere) exact_sphere<ANY>(s, ray, pend0, h, n_exact, nan_count);
-                if (pend1 != kNoSphere) exact_sphere<ANY>(s, ray, pend1, h, n_exact, nan_count);
+                const uint32_t first = pend0 != kNoSphere ? pend0 : pend1;
+                const uint32_t second = pend0 != kNoSphere ? pend1 : kNoSphere;
+                exact_sphere<ANY>(s, ray, first, h, n_exact, nan_count);
+                if (second != kNoSphere) exact_sphere<ANY>(s, ray, second, h, n_exact, nan_count);
                 pend0 = pend1 = kNoSphere;
                 boundf = h.bound() - t0f;
             }

@@ -413,7 +413,7 @@ template <bool ANY>
 __global__ void __launch_bounds__(128) k_verify_trace(const DScene s, const TraceArgs a, int level) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    const uint32_t pi = phys_index(a, i);
+    const uint32_t pi = phys_index(a.seg_len, a.seg_stride, i);
     const Ray ray = load_ray(a.q, pi);
     const Nearest h = trace_exact_all(s, ray, a.ctr);
     bool bad;
@@ -432,9 +432,10 @@ __global__ void __launch_bounds__(128) k_verify_trace(const DScene s, const Trac
     }
 }
 
-// shadow-queue order: hit-major (the L rays of a hit adjacent; default) or light-major (experiment)
+// shadow-queue order: light-major (one segment per light: neighbouring lanes trace neighbouring hits towards
+// the same light; default) or hit-major (the L rays of a hit adjacent; RG_SHADOW_LIGHT_MAJOR=0, for comparison)
 static bool shadow_light_major() {
-    static const bool v = [] { const char *e = getenv("RG_SHADOW_LIGHT_MAJOR"); return e && atoi(e) != 0; }();
+    static const bool v = [] { const char *e = getenv("RG_SHADOW_LIGHT_MAJOR"); return !e || atoi(e) != 0; }();
     return v;
 }
 
@@ -501,7 +502,7 @@ static int launch_trace(rg_scene *sc, const TraceArgs &ta, bool use_grid, cudaSt
     if (use_grid) {
         // persistent warps: enough blocks to fill the chip, each pulling rays from ctr->fetch
         const unsigned want = (ta.n + kGridTraceThreads - 1) / kGridTraceThreads;
-        static const int bps = [] { const char *e = getenv("RG_GRID_BPS"); return e ? atoi(e) : 6; }();
+        static const int bps = [] { const char *e = getenv("RG_GRID_BPS"); return e ? atoi(e) : RG_GRID_MINB; }();
         static const int t_refill = [] { const char *e = getenv("RG_GRID_REFILL"); return e ? atoi(e) : kGridRefill; }();
         static const int t_quorum = [] { const char *e = getenv("RG_GRID_QUORUM"); return e ? atoi(e) : kGridExactQuorum; }();
         static const int t_burst = [] { const char *e = getenv("RG_GRID_BURST"); return e ? atoi(e) : kGridScanBurst; }();
@@ -925,8 +926,9 @@ static int enqueue_batch_dev(rg_scene *sc, const DevPlan &plan, uint32_t width, 
         lb.lit_node = wf.lit_node[p].as<uint32_t>();
         lb.n = cap;
         lb.n_dev = &dc->lvl[d].n;
-        lb.shadow_sl = 1u;    // hit-major shadow queue
-        lb.shadow_sj = L;
+        const bool light_major = shadow_light_major();
+        lb.shadow_sl = light_major ? cap : 1u;   // one segment of `cap` slots per light, or the L rays of a hit adjacent
+        lb.shadow_sj = light_major ? 1u : L;
         lb.can_spawn = can_spawn ? 1u : 0u;
         lb.q_next = &dc->lvl[d + 1].n;
         lb.q_lit = &dc->lvl[d].n_lit;
@@ -972,6 +974,8 @@ static int enqueue_batch_dev(rg_scene *sc, const DevPlan &plan, uint32_t width, 
             sa.n = cap * L;
             sa.n_dev = &dc->lvl[d].n_lit;
             sa.n_mul = L;
+            sa.seg_len_dev = light_major ? &dc->lvl[d].n_lit : nullptr;
+            sa.seg_stride = cap;
             sa.void_flag = &dc->overflow;
             sa.fetch = &dc->lvl[d].fetch_shadow;
             sa.out_lit = wf.s_lit[p].as<uint8_t>();
@@ -1106,7 +1110,7 @@ int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0,
     for (;;) {   // a ray tree larger than device memory restarts the render with half the rows per batch
         // host-free loop (device-sized launches, no synchronisation inside the frame) unless switched off,
         // or this scene once outgrew the default queue capacities, or a debug mode needs the host in the loop
-        const bool host_free = sc->host_free != 1 && !sc->host_free_overflowed && sc->verify_cull < 2 && !shadow_light_major();
+        const bool host_free = sc->host_free != 1 && !sc->host_free_overflowed && sc->verify_cull < 2;
         *st = st0;
         events.used = 0;
         sync_events.used = 0;
@@ -1154,7 +1158,7 @@ int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0,
         }
         break;
     }
-    st->host_free = (sc->host_free != 1 && !sc->host_free_overflowed && sc->verify_cull < 2 && !shadow_light_major()) ? 1u : 0u;
+    st->host_free = (sc->host_free != 1 && !sc->host_free_overflowed && sc->verify_cull < 2) ? 1u : 0u;
     float ms = 0.f;
     RG_CUDA(cudaEventElapsedTime(&ms, sc->ev[0], sc->ev[1]));
     st->ms_device = ms;
