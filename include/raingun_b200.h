@@ -48,8 +48,14 @@ enum {
     RG_E_CUDA = -5,       /* CUDA runtime failure / no usable device            */
     RG_E_NOMEM = -6,      /* device or host allocation failed                   */
     RG_E_CANCELLED = -7,  /* streaming callback asked to stop (rendering.rs:53-54,67) */
-    RG_E_LIGHTS = -8      /* more than RG_MAX_LIGHTS lights                     */
+    RG_E_LIGHTS = -8,     /* more than RG_MAX_LIGHTS lights                     */
+    RG_E_BUSY = -9        /* the handle is already rendering on another thread (the reference's &Scene
+                             is Sync; a device scene owns its scratch: one render at a time per handle) */
 };
+
+/* `device` value for rg_scene_create: upload to EVERY visible GPU; renders are then split into row
+ * tiles across them inside the library (rayon's par_iter, rendering.rs:27-35). */
+#define RG_DEVICE_ALL (-1)
 
 /* ---- enums mirroring the reference's serde enums --------------------------- */
 enum { RG_BODY_SPHERE = 0, RG_BODY_PLANE = 1, RG_BODY_DISK = 2, RG_BODY_AABB = 3 }; /* bodies.rs:41-47 */
@@ -110,8 +116,10 @@ typedef struct rg_scene_desc {
 
 /* Which device pipeline renders (all are bit-identical in their output). */
 enum {
-    RG_PIPELINE_WAVEFRONT = 0, /* per-bounce ray queues (default)                 */
-    RG_PIPELINE_MEGAKERNEL = 1 /* one thread per pixel, explicit stack (validation) */
+    RG_PIPELINE_WAVEFRONT = 0, /* per-bounce ray queues                            */
+    RG_PIPELINE_MEGAKERNEL = 1,/* one thread per pixel, explicit stack, every body tested in FP64 */
+    RG_PIPELINE_AUTO = 2       /* default: the megakernel for scenes of a handful of bodies (the shipped
+                                  examples: no queue traffic at all, 2-3x faster there), else the wavefront */
 };
 /* How `Scene::trace` is evaluated (results identical). */
 enum {
@@ -134,8 +142,12 @@ enum {
     RG_OPT_GRAPH = 8,        /* replay the host-free frame as one CUDA graph: 0 = automatic, 1 = off, 2 = on */
     RG_OPT_TRACE_STATS = 9,  /* 1 = the grid tracer counts cells / fetches / cull tests / lane use
                                 (rg_stats.grid_*); an instrumented kernel, slower; results unchanged */
-    RG_OPT_REORDER = 10      /* bin every level's children by origin region and direction octant before they
-                                are traced (host-free loop, grid tracer): 0 = automatic (on), 1 = off, 2 = on */
+    RG_OPT_REORDER = 10,     /* bin every level's children by origin region and direction octant before they
+                                are traced (host-free loop, grid tracer): 0 = automatic (off: it does not pay),
+                                1 = off, 2 = on */
+    RG_OPT_SCHEDULE = 11,    /* multi-GPU scenes: 0 = automatic, 1 = static (tile t on device t mod N),
+                                2 = static share + a stealable tail handed out by an atomic tile counter */
+    RG_OPT_TILE_ROWS = 12    /* multi-GPU scenes: rows per tile (default 8) */
 };
 
 /* Counters and timings of one render call.  A "ray" is one `Scene::trace`
@@ -168,6 +180,8 @@ typedef struct rg_stats {
     uint64_t grid_refills;         /* warp refills from the ray counter              */
     uint64_t grid_lane_steps;      /* lanes doing scan work, summed over scan iterations */
     uint64_t grid_lane_slots;      /* 32 x scan iterations (the denominator)         */
+    uint32_t pipeline_used;        /* RG_PIPELINE_WAVEFRONT | RG_PIPELINE_MEGAKERNEL */
+    uint32_t devices_used;         /* GPUs that rendered rows of this call (multi-GPU scenes) */
 } rg_stats;
 
 typedef struct rg_scene rg_scene;
@@ -183,6 +197,14 @@ typedef int (*rg_rows_cb)(uint32_t y0, uint32_t rows, uint32_t width,
  * exact-culling grid.  Replaces the serde construction of `Scene`
  * (scene.rs:11-31) + `load_texture` (material.rs:34-47) as the upload layer. */
 int rg_scene_create(const rg_scene_desc *desc, int32_t device, rg_scene **out);
+/* The same on an explicit list of devices (n_devices >= 1; a device listed twice gets two lanes).  With more than one device the
+ * handle spans them: rg_render / rg_render_rows / rg_render_stream cut the image into row tiles, one
+ * library thread per GPU renders the tiles it owns or claims from the shared tile counter and copies its
+ * rows over its own PCIe link into the caller's buffer.  The *_device entry points need a single-device
+ * handle. */
+int rg_scene_create_multi(const rg_scene_desc *desc, const int32_t *devices, uint32_t n_devices, rg_scene **out);
+/* GPUs a handle spans (1 for rg_scene_create on one device). */
+int rg_scene_device_count(const rg_scene *scene);
 void rg_scene_destroy(rg_scene *scene);
 int rg_scene_set_option(rg_scene *scene, int32_t key, int64_t value);
 

@@ -18,6 +18,8 @@ pub const RG_E_CUDA: c_int = -5;
 pub const RG_E_NOMEM: c_int = -6;
 pub const RG_E_CANCELLED: c_int = -7; // closed channel, rendering.rs:53-54,67
 pub const RG_E_LIGHTS: c_int = -8;
+pub const RG_E_BUSY: c_int = -9;
+pub const RG_DEVICE_ALL: i32 = -1;
 
 pub const RG_BODY_SPHERE: u8 = 0;
 pub const RG_BODY_PLANE: u8 = 1;
@@ -41,6 +43,8 @@ pub const RG_OPT_HOST_FREE: i32 = 7;
 pub const RG_OPT_GRAPH: i32 = 8;
 pub const RG_OPT_TRACE_STATS: i32 = 9;
 pub const RG_OPT_REORDER: i32 = 10;
+pub const RG_OPT_SCHEDULE: i32 = 11;
+pub const RG_OPT_TILE_ROWS: i32 = 12;
 
 #[repr(C)]
 pub struct rg_texture_desc {
@@ -104,6 +108,8 @@ pub struct rg_stats {
     pub grid_refills: u64,
     pub grid_lane_steps: u64,
     pub grid_lane_slots: u64,
+    pub pipeline_used: u32,
+    pub devices_used: u32,
 }
 
 pub enum rg_scene {}
@@ -113,6 +119,9 @@ pub type rg_rows_cb =
 
 extern "C" {
     pub fn rg_scene_create(desc: *const rg_scene_desc, device: i32, out: *mut *mut rg_scene) -> c_int;
+    pub fn rg_scene_create_multi(desc: *const rg_scene_desc, devices: *const i32, n_devices: u32,
+                                 out: *mut *mut rg_scene) -> c_int;
+    pub fn rg_scene_device_count(scene: *const rg_scene) -> c_int;
     pub fn rg_scene_destroy(scene: *mut rg_scene);
     pub fn rg_scene_set_option(scene: *mut rg_scene, key: i32, value: i64) -> c_int;
     pub fn rg_render(scene: *mut rg_scene, width: u32, height: u32, rgba_out: *mut u8,

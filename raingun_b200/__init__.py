@@ -19,13 +19,13 @@ from typing import Callable, Optional
 import numpy as np
 
 from . import _native
-from ._native import (ACCEL_AUTO, ACCEL_BRUTE, ACCEL_GRID, PIPELINE_MEGAKERNEL, PIPELINE_WAVEFRONT,
+from ._native import (ACCEL_AUTO, ACCEL_BRUTE, ACCEL_GRID, DEVICE_ALL, PIPELINE_AUTO, PIPELINE_MEGAKERNEL, PIPELINE_WAVEFRONT,
                       RaingunError)
 from .scene import SceneData, SceneError, Stats, load_scene, parse_scene, scene_from_dict
 
 __all__ = ["Scene", "SharedFrame", "SceneData", "SceneError", "RaingunError", "Stats", "load_scene", "parse_scene",
            "scene_from_dict", "device_count", "measure_peaks", "ACCEL_AUTO", "ACCEL_BRUTE", "ACCEL_GRID",
-           "PIPELINE_WAVEFRONT", "PIPELINE_MEGAKERNEL"]
+           "PIPELINE_WAVEFRONT", "PIPELINE_MEGAKERNEL", "PIPELINE_AUTO", "DEVICE_ALL"]
 
 
 def device_count() -> int:
@@ -71,16 +71,26 @@ class SharedFrame:
 
 
 class Scene:
-    """A scene resident on one GPU (the uploaded counterpart of raingun-lib's ``Scene``)."""
+    """A scene resident on one GPU — or on several (``device=DEVICE_ALL`` / ``devices=[...]``): renders into
+    host memory are then split into row tiles across the GPUs inside the library (rayon's ``par_iter``,
+    rendering.rs:27-35).  The uploaded counterpart of raingun-lib's ``Scene``."""
 
-    def __init__(self, data: SceneData, device: int = 0) -> None:
+    def __init__(self, data: SceneData, device: int = 0, devices=None) -> None:
         self.data = data
         self.device = device
         self._h = ctypes.c_void_p()
         self.last_stats = Stats()
         desc, keep = data.to_desc()
-        _native.check(_native.lib().rg_scene_create(ctypes.byref(desc), device, ctypes.byref(self._h)))
+        if devices is not None:
+            arr = (ctypes.c_int32 * len(devices))(*devices)
+            _native.check(_native.lib().rg_scene_create_multi(ctypes.byref(desc), arr, len(devices), ctypes.byref(self._h)))
+        else:
+            _native.check(_native.lib().rg_scene_create(ctypes.byref(desc), device, ctypes.byref(self._h)))
         del keep
+
+    @property
+    def device_count(self) -> int:
+        return int(_native.lib().rg_scene_device_count(self._h))
 
     # -- construction, as src/main.rs:117-125 does it
     @classmethod

@@ -17,19 +17,20 @@ LIB_PATH = os.environ.get("RAINGUN_B200_LIB") or os.path.join(_HERE, "libraingun
 
 RG_OK = 0
 ERRORS = {0: "RG_OK", -1: "RG_E_INVALID", -2: "RG_E_PORTRAIT", -3: "RG_E_TOO_LARGE", -4: "RG_E_DEPTH",
-          -5: "RG_E_CUDA", -6: "RG_E_NOMEM", -7: "RG_E_CANCELLED", -8: "RG_E_LIGHTS"}
-E_INVALID, E_PORTRAIT, E_TOO_LARGE, E_DEPTH, E_CUDA, E_NOMEM, E_CANCELLED, E_LIGHTS = -1, -2, -3, -4, -5, -6, -7, -8
+          -5: "RG_E_CUDA", -6: "RG_E_NOMEM", -7: "RG_E_CANCELLED", -8: "RG_E_LIGHTS", -9: "RG_E_BUSY"}
+E_INVALID, E_PORTRAIT, E_TOO_LARGE, E_DEPTH, E_CUDA, E_NOMEM, E_CANCELLED, E_LIGHTS, E_BUSY = -1, -2, -3, -4, -5, -6, -7, -8, -9
+DEVICE_ALL = -1
 
-PIPELINE_WAVEFRONT, PIPELINE_MEGAKERNEL = 0, 1
+PIPELINE_WAVEFRONT, PIPELINE_MEGAKERNEL, PIPELINE_AUTO = 0, 1, 2
 ACCEL_AUTO, ACCEL_BRUTE, ACCEL_GRID = 0, 1, 2
 OPT_PIPELINE, OPT_ACCEL, OPT_MAX_DEPTH, OPT_BATCH_PIXELS, OPT_VERIFY_CULL, OPT_OVERLAP = 1, 2, 3, 4, 5, 6
-OPT_HOST_FREE, OPT_GRAPH, OPT_TRACE_STATS, OPT_REORDER = 7, 8, 9, 10
+OPT_HOST_FREE, OPT_GRAPH, OPT_TRACE_STATS, OPT_REORDER, OPT_SCHEDULE, OPT_TILE_ROWS = 7, 8, 9, 10, 11, 12
 
 ROWS_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                            ctypes.POINTER(ctypes.c_uint8), ctypes.c_void_p)
 
 # every symbol include/raingun_b200.h declares
-EXPORTS = ("rg_scene_create", "rg_scene_destroy", "rg_scene_set_option", "rg_render", "rg_render_rows",
+EXPORTS = ("rg_scene_create", "rg_scene_create_multi", "rg_scene_device_count", "rg_scene_destroy", "rg_scene_set_option", "rg_render", "rg_render_rows",
            "rg_render_rows_device", "rg_render_rowlist_device", "rg_render_rowlist_scatter", "rg_shared_frame_create",
            "rg_shared_frame_open", "rg_shared_frame_close", "rg_render_stream", "rg_last_error", "rg_measure_peaks",
            "rg_device_count")
@@ -56,6 +57,10 @@ def lib() -> ctypes.CDLL:
     vp, u32, i32 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int32
     L.rg_scene_create.restype = ctypes.c_int
     L.rg_scene_create.argtypes = [ctypes.POINTER(SceneDesc), i32, ctypes.POINTER(vp)]
+    L.rg_scene_create_multi.restype = ctypes.c_int
+    L.rg_scene_create_multi.argtypes = [ctypes.POINTER(SceneDesc), ctypes.POINTER(i32), u32, ctypes.POINTER(vp)]
+    L.rg_scene_device_count.restype = ctypes.c_int
+    L.rg_scene_device_count.argtypes = [vp]
     L.rg_scene_destroy.restype = None
     L.rg_scene_destroy.argtypes = [vp]
     L.rg_scene_set_option.restype = ctypes.c_int

@@ -17,6 +17,7 @@
 
 namespace rg {
 
+constexpr uint32_t kMegaAutoBodies = 16;
 static thread_local std::string g_last_error;
 static double g_last_ffma2_tflops = 0.0, g_last_ffma_tflops = 0.0;   // rg_measure_peaks detail
 
@@ -387,6 +388,7 @@ int rg_device_count(void) {
 
 void rg_scene_destroy(rg_scene *sc) {
     if (!sc) return;
+    if (sc->multi) { multi_destroy(sc); return; }
     cudaSetDevice(sc->device);
     sc->graphs.release();
     for (auto o : sc->tex_objs) cudaDestroyTextureObject(o);
@@ -442,6 +444,15 @@ int rg_scene_create(const rg_scene_desc *desc, int32_t device, rg_scene **out) {
         cudaGetLastError();
         set_error("no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(e));
         return RG_E_CUDA;
+    }
+    if (device == RG_DEVICE_ALL) {   // every visible GPU (RG_DEVICES=n: the first n)
+        const char *e = getenv("RG_DEVICES");
+        int n = e ? atoi(e) : ndev;
+        if (n < 1 || n > ndev) n = ndev;
+        std::vector<int32_t> all((size_t)n);
+        for (int k = 0; k < n; ++k) all[(size_t)k] = k;
+        if (n == 1) return rg_scene_create(desc, 0, out);
+        return multi_create(desc, all.data(), (uint32_t)n, out);
     }
     if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return RG_E_INVALID; }
     RG_CUDA(cudaSetDevice(device));
@@ -506,9 +517,13 @@ int rg_scene_create(const rg_scene_desc *desc, int32_t device, rg_scene **out) {
 
 int rg_scene_set_option(rg_scene *sc, int32_t key, int64_t value) {
     if (!sc) { set_error("scene is NULL"); return RG_E_INVALID; }
+    if (sc->multi) return multi_set_option(sc, key, value);
     switch (key) {
+        case RG_OPT_SCHEDULE:    // multi-GPU scenes only; accepted and ignored on one device
+        case RG_OPT_TILE_ROWS:
+            return RG_OK;
         case RG_OPT_PIPELINE:
-            if (value != RG_PIPELINE_WAVEFRONT && value != RG_PIPELINE_MEGAKERNEL) break;
+            if (value != RG_PIPELINE_WAVEFRONT && value != RG_PIPELINE_MEGAKERNEL && value != RG_PIPELINE_AUTO) break;
             sc->pipeline = (int)value;
             return RG_OK;
         case RG_OPT_ACCEL:
@@ -602,26 +617,40 @@ static int render_device(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint
     rg_stats local;
     std::memset(&local, 0, sizeof(local));
     int rc;
-    if (sc->pipeline == RG_PIPELINE_MEGAKERNEL) rc = mega_render(sc, w, h, y0, y1, d_rows, (uchar4 *)d_rgba_out, stream, &local);
+    // RG_PIPELINE_AUTO: with a handful of bodies the per-pixel recursion (every body tested in FP64, no queues)
+    // beats the wavefront at every image size (measured on the shipped examples, 800x600 .. 4K: 2-3x);
+    // the crossover lies near kMegaAutoBodies bodies (RG_MEGA_AUTO_BODIES for tuning runs)
+    static const uint32_t mega_auto_bodies = [] { const char *e = getenv("RG_MEGA_AUTO_BODIES"); return e ? (uint32_t)atoi(e) : kMegaAutoBodies; }();
+    const bool mega = sc->pipeline == RG_PIPELINE_MEGAKERNEL ||
+                      (sc->pipeline == RG_PIPELINE_AUTO && !sc->scatter_out && sc->n_bodies <= mega_auto_bodies && sc->verify_cull == 0);
+    if (mega) rc = mega_render(sc, w, h, y0, y1, d_rows, (uchar4 *)d_rgba_out, stream, &local);
     else rc = wavefront_render(sc, w, h, y0, y1, d_rows, (uchar4 *)d_rgba_out, stream, &local);
+    local.pipeline_used = mega ? RG_PIPELINE_MEGAKERNEL : RG_PIPELINE_WAVEFRONT;
     local.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (stats) *stats = local;
     return rc;
 }
 
-int rg_render_rows_device(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, void *d_rgba_out,
+static int single_device_only(const rg_scene *sc, const char *what) {
+    if (sc && sc->multi) { set_error("%s needs a single-device scene (this one spans %u GPUs)", what, multi_device_count(sc)); return RG_E_INVALID; }
+    return RG_OK;
+}
+
+static int rg_render_rows_device_impl(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, void *d_rgba_out,
                           void *cuda_stream, rg_stats *stats) {
     int rc = check_dims(sc, w, h, y0, y1);
     if (rc) return rc;
+    if ((rc = single_device_only(sc, "rg_render_rows_device"))) return rc;
     if (!d_rgba_out && y1 > y0) { set_error("output pointer is NULL"); return RG_E_INVALID; }
     RG_CUDA(cudaSetDevice(sc->device));
     return render_device(sc, w, h, y0, y1, nullptr, d_rgba_out, reinterpret_cast<cudaStream_t>(cuda_stream), stats);
 }
 
-int rg_render_rowlist_device(rg_scene *sc, uint32_t w, uint32_t h, const uint32_t *rows, uint32_t n_rows,
+static int rg_render_rowlist_device_impl(rg_scene *sc, uint32_t w, uint32_t h, const uint32_t *rows, uint32_t n_rows,
                              void *d_rgba_out, void *cuda_stream, rg_stats *stats) {
     int rc = check_dims(sc, w, h, 0, h);
     if (rc) return rc;
+    if ((rc = single_device_only(sc, "rg_render_rowlist_device"))) return rc;
     if (n_rows && (!rows || !d_rgba_out)) { set_error("rows / output pointer is NULL"); return RG_E_INVALID; }
     for (uint32_t k = 0; k < n_rows; ++k)
         if (rows[k] >= h) { set_error("rows[%u] = %u is outside the image (height %u)", k, rows[k], h); return RG_E_INVALID; }
@@ -635,12 +664,12 @@ int rg_render_rowlist_device(rg_scene *sc, uint32_t w, uint32_t h, const uint32_
     return render_device(sc, w, h, 0, n_rows, sc->rowlist.as<uint32_t>(), d_rgba_out, stream, stats);
 }
 
-int rg_render_rowlist_scatter(rg_scene *sc, uint32_t w, uint32_t h, const uint32_t *rows, uint32_t n_rows,
+static int rg_render_rowlist_scatter_impl(rg_scene *sc, uint32_t w, uint32_t h, const uint32_t *rows, uint32_t n_rows,
                               void *d_frame, void *cuda_stream, rg_stats *stats) {
-    if (sc && sc->pipeline != RG_PIPELINE_WAVEFRONT) { set_error("rg_render_rowlist_scatter needs the wavefront pipeline"); return RG_E_INVALID; }
+    if (sc && sc->pipeline == RG_PIPELINE_MEGAKERNEL) { set_error("rg_render_rowlist_scatter needs the wavefront pipeline"); return RG_E_INVALID; }
     if (!sc) { set_error("scene is NULL"); return RG_E_INVALID; }
     sc->scatter_out = true;
-    const int rc = rg_render_rowlist_device(sc, w, h, rows, n_rows, d_frame, cuda_stream, stats);
+    const int rc = rg_render_rowlist_device_impl(sc, w, h, rows, n_rows, d_frame, cuda_stream, stats);
     sc->scatter_out = false;
     return rc;
 }
@@ -680,17 +709,18 @@ int rg_shared_frame_close(int32_t device, void *d_ptr, int32_t is_owner) {
     return RG_OK;
 }
 
-int rg_render_rows(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, uint8_t *rgba_out, rg_stats *stats) {
+static int rg_render_rows_impl(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, uint8_t *rgba_out, rg_stats *stats) {
     int rc = check_dims(sc, w, h, y0, y1);
     if (rc) return rc;
     if (!rgba_out && y1 > y0) { set_error("output pointer is NULL"); return RG_E_INVALID; }
+    if (sc->multi) return multi_render_rows(sc, w, h, y0, y1, rgba_out, stats);   // every GPU of the scene takes its row tiles
     auto t0 = std::chrono::steady_clock::now();
     RG_CUDA(cudaSetDevice(sc->device));
     const size_t bytes = (size_t)(y1 - y0) * w * 4;
     if ((rc = sc->frame.reserve(bytes ? bytes : 4))) return rc;
     rg_stats local;
     std::memset(&local, 0, sizeof(local));
-    rc = rg_render_rows_device(sc, w, h, y0, y1, sc->frame.ptr, sc->stream, &local);
+    rc = rg_render_rows_device_impl(sc, w, h, y0, y1, sc->frame.ptr, sc->stream, &local);
     if (rc) return rc;
     if (bytes) {
         RG_CUDA(cudaMemcpyAsync(rgba_out, sc->frame.ptr, bytes, cudaMemcpyDeviceToHost, sc->stream));
@@ -701,8 +731,8 @@ int rg_render_rows(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y
     return RG_OK;
 }
 
-int rg_render(rg_scene *sc, uint32_t w, uint32_t h, uint8_t *rgba_out, rg_stats *stats) {
-    return rg_render_rows(sc, w, h, 0, h, rgba_out, stats);
+static int rg_render_impl(rg_scene *sc, uint32_t w, uint32_t h, uint8_t *rgba_out, rg_stats *stats) {
+    return rg_render_rows_impl(sc, w, h, 0, h, rgba_out, stats);
 }
 
 static void accumulate(rg_stats *total, const rg_stats &s) {
@@ -722,6 +752,7 @@ static void accumulate(rg_stats *total, const rg_stats &s) {
     total->batches += s.batches;
     total->graph_replays += s.graph_replays;
     total->host_free = s.host_free;
+    total->pipeline_used = s.pipeline_used;
     total->grid_cells += s.grid_cells;
     total->grid_fetches += s.grid_fetches;
     total->grid_culls += s.grid_culls;
@@ -732,7 +763,7 @@ static void accumulate(rg_stats *total, const rg_stats &s) {
     total->accel_used = s.accel_used;
 }
 
-int rg_render_stream(rg_scene *sc, uint32_t w, uint32_t h, uint32_t band_rows, rg_rows_cb cb, void *user, rg_stats *stats) {
+static int rg_render_stream_impl(rg_scene *sc, uint32_t w, uint32_t h, uint32_t band_rows, rg_rows_cb cb, void *user, rg_stats *stats) {
     int rc = check_dims(sc, w, h, 0, h);
     if (rc) return rc;
     if (!cb) { set_error("callback is NULL"); return RG_E_INVALID; }
@@ -756,7 +787,7 @@ int rg_render_stream(rg_scene *sc, uint32_t w, uint32_t h, uint32_t band_rows, r
     for (uint32_t y0 = 0; y0 < h; y0 += band_rows) {
         uint32_t y1 = y0 + band_rows < h ? y0 + band_rows : h;
         rg_stats s;
-        rc = rg_render_rows(sc, w, h, y0, y1, sc->h_frame, &s);
+        rc = rg_render_rows_impl(sc, w, h, y0, y1, sc->h_frame, &s);
         if (rc) return rc;
         accumulate(&total, s);
         if (cb(y0, y1 - y0, w, sc->h_frame, user) != 0) {   // closed channel: rendering.rs:53-54,67
@@ -769,6 +800,62 @@ int rg_render_stream(rg_scene *sc, uint32_t w, uint32_t h, uint32_t band_rows, r
     total.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (stats) *stats = total;
     return RG_OK;
+}
+
+// ---- public render entry points: one call at a time per handle ---------------------------------------
+// The reference's &Scene is Sync; a device-side scene is not (its scratch queues belong to the handle), so a
+// second render on a handle that is already rendering is refused with RG_E_BUSY instead of corrupting both.
+struct BusyGuard {
+    rg_scene *sc;
+    bool ok;
+    explicit BusyGuard(rg_scene *s) : sc(s), ok(true) {
+        if (sc && sc->busy.exchange(true, std::memory_order_acquire)) {
+            ok = false;
+            set_error("this scene handle is already rendering on another thread (one render at a time per handle; create one handle per thread)");
+        }
+    }
+    ~BusyGuard() { if (sc && ok) sc->busy.store(false, std::memory_order_release); }
+};
+#define RG_ENTER(sc) BusyGuard _guard(sc); if (!_guard.ok) return RG_E_BUSY
+
+int rg_render_rows_device(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, void *d_rgba_out, void *cuda_stream, rg_stats *stats) {
+    RG_ENTER(sc);
+    return rg_render_rows_device_impl(sc, w, h, y0, y1, d_rgba_out, cuda_stream, stats);
+}
+int rg_render_rowlist_device(rg_scene *sc, uint32_t w, uint32_t h, const uint32_t *rows, uint32_t n_rows, void *d_rgba_out, void *cuda_stream, rg_stats *stats) {
+    RG_ENTER(sc);
+    return rg_render_rowlist_device_impl(sc, w, h, rows, n_rows, d_rgba_out, cuda_stream, stats);
+}
+int rg_render_rowlist_scatter(rg_scene *sc, uint32_t w, uint32_t h, const uint32_t *rows, uint32_t n_rows, void *d_frame, void *cuda_stream, rg_stats *stats) {
+    RG_ENTER(sc);
+    return rg_render_rowlist_scatter_impl(sc, w, h, rows, n_rows, d_frame, cuda_stream, stats);
+}
+int rg_render_rows(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, uint8_t *rgba_out, rg_stats *stats) {
+    RG_ENTER(sc);
+    return rg_render_rows_impl(sc, w, h, y0, y1, rgba_out, stats);
+}
+int rg_render(rg_scene *sc, uint32_t w, uint32_t h, uint8_t *rgba_out, rg_stats *stats) {
+    RG_ENTER(sc);
+    return rg_render_impl(sc, w, h, rgba_out, stats);
+}
+int rg_render_stream(rg_scene *sc, uint32_t w, uint32_t h, uint32_t band_rows, rg_rows_cb cb, void *user, rg_stats *stats) {
+    RG_ENTER(sc);
+    return rg_render_stream_impl(sc, w, h, band_rows, cb, user, stats);
+}
+
+int rg_scene_create_multi(const rg_scene_desc *desc, const int32_t *devices, uint32_t n_devices, rg_scene **out) {
+    if (!out) { set_error("out is NULL"); return RG_E_INVALID; }
+    *out = nullptr;
+    if (!devices || n_devices == 0) { set_error("no devices given"); return RG_E_INVALID; }
+    if (n_devices == 1) return rg_scene_create(desc, devices[0], out);
+    int rc = validate(desc);   // (a device listed twice simply gets two lanes: its own scene copy, stream and thread each)
+    if (rc) return rc;
+    return multi_create(desc, devices, n_devices, out);
+}
+
+int rg_scene_device_count(const rg_scene *sc) {
+    if (!sc) return 0;
+    return sc->multi ? (int)multi_device_count(sc) : 1;
 }
 
 int rg_measure_peaks(int32_t device, double *fp32_tflops, double *fp64_tflops, double *sm_clock_mhz) {

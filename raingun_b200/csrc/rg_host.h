@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <string>
@@ -81,8 +82,12 @@ struct GraphCache {
 
 }  // namespace rg
 
+namespace rg { struct MultiState; }
+
 struct rg_scene {
     int device = 0;
+    rg::MultiState *multi = nullptr;       // set: this handle spans several GPUs (rg_multi.cu) and owns no device state itself
+    std::atomic<bool> busy{false};         // a render call is running on this handle (second callers get RG_E_BUSY)
     rg::DScene ds{};                    // device pointers inside
     rg::SceneArena arena;               // scene arrays
     std::vector<cudaTextureObject_t> tex_objs;
@@ -97,7 +102,7 @@ struct rg_scene {
     rg::WavefrontScratch wf;
     rg::GraphCache graphs;                 // dies with the scene (kernel parameters hold scene pointers by value)
     // options
-    int pipeline = RG_PIPELINE_WAVEFRONT;
+    int pipeline = RG_PIPELINE_AUTO;
     int accel = RG_ACCEL_AUTO;
     uint32_t scene_max_depth = 0;          // as given in the desc
     uint64_t batch_pixels = 0;
@@ -107,6 +112,7 @@ struct rg_scene {
     int graph = 0;                         // RG_OPT_GRAPH: 0 auto, 1 off, 2 on
     int reorder = 0;                       // RG_OPT_REORDER: 0 auto (on with the grid tracer), 1 off, 2 on
     bool trace_stats = false;              // RG_OPT_TRACE_STATS
+    uint32_t depth_hint = 0;               // levels the ray tree of this scene has been seen to use (0 = unknown)
     bool host_free_overflowed = false;     // a level once outgrew the default queue capacity: stay with the host-sized loop
     bool scatter_out = false;              // this call stores rows at their place in a full frame (rg_render_rowlist_scatter)
     // derived
@@ -119,6 +125,12 @@ namespace rg {
 // rows [y0, y1) of the image, or — when d_rows is given — entries [y0, y1) of that row list
 int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0, uint32_t y1,
                      const uint32_t *d_rows, uchar4 *d_out, cudaStream_t stream, rg_stats *st);
+// rg_multi.cu
+int multi_create(const rg_scene_desc *desc, const int32_t *devices, uint32_t n_devices, rg_scene **out);
+void multi_destroy(rg_scene *sc);
+int multi_set_option(rg_scene *sc, int32_t key, int64_t value);
+uint32_t multi_device_count(const rg_scene *sc);
+int multi_render_rows(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, uint8_t *rgba_out, rg_stats *stats);
 // rg_grid.cu
 int grid_build(rg_scene *sc, const std::vector<double> &sph /* n x 4 */, const std::vector<float4> &cull);
 }  // namespace rg

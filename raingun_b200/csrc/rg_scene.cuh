@@ -104,6 +104,8 @@ struct DCounters {
     // ---- host-free loop
     unsigned int overflow;             // a level outgrew its queue capacity: the frame is void, the host re-renders
     unsigned int max_level;            // deepest level that held a ray
+    unsigned int deeper;               // the last enqueued level emitted children (depth hint too small): frame void
+    unsigned int pad_;
     unsigned long long grid_cells;     // RG_OPT_TRACE_STATS: cells visited / records fetched / cull tests / refills
     unsigned long long grid_fetches;
     unsigned long long grid_culls;

@@ -77,6 +77,7 @@ struct LevelBuffers {
     unsigned int *void_flag;         // set when a queue overflows; once set, every later launch does nothing
     uint32_t level;                  // recursion depth of this level
     uint32_t count_on_device;        // shadow rays / deepest level are counted in DCounters (host-free loop)
+    uint32_t last_enqueued;          // no launch follows for this level's children (depth hint): flag them
     // ray reordering (see k_bin_scatter): `next` is then a staging queue, and per child k_shade also leaves
     uint32_t *next_key;              // ... its bin,
     uint32_t *next_meta;             // ... its parent node (bit 31: it is the transmission child),
@@ -200,11 +201,17 @@ __global__ void __launch_bounds__(256) k_shade(const DScene s, const LevelBuffer
     if (threadIdx.x == 0) {
         const uint32_t n_lit_b = sh_cnt[0], n_next_b = sh_cnt[1], n_trans_b = sh_cnt[2];
         sh_base[0] = n_lit_b ? atomicAdd(lb.q_lit, n_lit_b) : 0u;
-        sh_base[1] = n_next_b ? atomicAdd(lb.q_next, n_next_b) : 0u;
         sh_drop = 0u;
-        if (n_next_b && (uint64_t)sh_base[1] + n_next_b > lb.cap_next) {   // only possible with device-sized queues
+        if (lb.last_enqueued) {   // depth hint: nobody will trace this level's children — they must not exist
+            sh_base[1] = 0u;
             sh_drop = 1u;
-            atomicExch(lb.void_flag, 1u);
+            if (n_next_b) ctr->deeper = 1u;   // the host repeats the frame with every level
+        } else {
+            sh_base[1] = n_next_b ? atomicAdd(lb.q_next, n_next_b) : 0u;
+            if (n_next_b && (uint64_t)sh_base[1] + n_next_b > lb.cap_next) {   // only possible with device-sized queues
+                sh_drop = 1u;
+                atomicExch(lb.void_flag, 1u);
+            }
         }
         if (n_next_b - n_trans_b) atomicAdd(&ctr->rays[2], (unsigned long long)(n_next_b - n_trans_b));
         if (n_trans_b) atomicAdd(&ctr->rays[3], (unsigned long long)n_trans_b);
@@ -527,12 +534,12 @@ static int launch_trace(rg_scene *sc, const TraceArgs &ta, bool use_grid, cudaSt
         }
 #define RG_LAUNCH_RESIDENT(R_, U_, T_, PF_)                                                                                   \
     do {                                                                                                                      \
-        static uint64_t attr_set = 0; /* per device: the attribute belongs to the device's copy of the function */          \
+        static std::atomic<uint64_t> attr_set{0}; /* per device: the attribute belongs to the device's copy of the function */ \
         const uint64_t dev_bit = 1ull << (sc->device & 63);                                                                   \
-        if (!(attr_set & dev_bit)) {                                                                                          \
+        if (!(attr_set.load() & dev_bit)) {                                                                                   \
             RG_CUDA(cudaFuncSetAttribute(k_trace_brute_resident<ANY, R_, U_, T_, PF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          kResidentSmemMax));                                                                  \
-            attr_set |= dev_bit;                                                                                              \
+            attr_set.fetch_or(dev_bit);                                                                                       \
         }                                                                                                                     \
         const uint64_t tiles = ((uint64_t)ta.n + 32 * R_ - 1) / (32 * R_);                                                     \
         const unsigned blocks = (unsigned)std::min<uint64_t>((uint64_t)sc->sm_count, (tiles + (T_ / 32) - 1) / (T_ / 32));      \
@@ -824,7 +831,12 @@ static int plan_batch_dev(rg_scene *sc, uint32_t npix, DevPlan &plan, bool use_g
     const DScene &ds = sc->ds;
     const uint32_t L = ds.n_lights;
     WavefrontScratch &wf = sc->wf;
+    // Levels to enqueue: all the recursion depth allows, or — once a frame of this scene has shown how deep
+    // its ray tree really goes — just those (a shallow scene with the default depth of 10 would otherwise pay
+    // for dozens of empty launches).  The frame is checked afterwards: the last enqueued level must not have
+    // emitted children (wavefront_render), else it is repeated with every level.
     plan.levels = std::max<uint32_t>(ds.max_depth, 1u);
+    if (sc->depth_hint && sc->depth_hint < plan.levels) plan.levels = sc->depth_hint;
     uint64_t cap_max[2] = {0, 0}, cap_all = 0;
     for (uint32_t d = 0; d < plan.levels; ++d) {
         const uint64_t c = d == 0 ? npix : std::min<uint64_t>(2ull * plan.cap[d - 1], (uint64_t)kLevelGrowth * npix);
@@ -936,6 +948,7 @@ static int enqueue_batch_dev(rg_scene *sc, const DevPlan &plan, uint32_t width, 
         lb.void_flag = &dc->overflow;
         lb.level = d;
         lb.count_on_device = 1u;
+        lb.last_enqueued = (d + 1 == plan.levels && can_spawn) ? 1u : 0u;
         const RayQueue next_sorted = lb.next;
         unsigned int *bin_count = nullptr, *bin_base = nullptr, *bin_cursor = nullptr;
         const bool bin_this = reorder && can_spawn;
@@ -1156,7 +1169,17 @@ int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0,
             sc->host_free_overflowed = true;
             continue;
         }
+        if (host_free && sc->depth_hint && sc->depth_hint < std::max<uint32_t>(sc->ds.max_depth, 1u) &&
+            sc->h_counters->deeper) {   // the ray tree went deeper than the hint: repeat with every level
+            sc->depth_hint = 0;
+            continue;
+        }
         break;
+    }
+    // what the next frame of this scene may assume about the depth of the ray tree
+    {
+        const uint32_t used = std::max(st->max_level, sc->h_counters->max_level) + 1u;
+        sc->depth_hint = std::max(sc->depth_hint, used);
     }
     st->host_free = (sc->host_free != 1 && !sc->host_free_overflowed && sc->verify_cull < 2) ? 1u : 0u;
     float ms = 0.f;

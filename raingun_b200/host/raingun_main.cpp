@@ -57,6 +57,8 @@ const char kUsage[] =
     "        --hd         Renders in 1080 (HD) resolution. Explicit width/height overrides.\n"
     "        --help       Prints help information\n"
     "        --preview    Streams finished row bands while rendering.\n"
+    "        --gpus <N>   Render on N GPUs of this machine (0 or 'all' = every visible GPU; default 1;\n"
+    "                     the image is split into row tiles inside the library). B200 path only.\n"
     "    -V, --version    Prints version information\n\nOPTIONS:\n"
     "    -h, --height <PIXELS>      Height of output image.\n"
     "    -o, --output <FILENAME>    Specify filename of the rendered image.\n"
@@ -76,6 +78,23 @@ int main(int argc, char **argv) {
             return 0;
         }
     }
+    // --gpus N is this binary's own option (the reference has one machine's CPU cores instead): take it out
+    // of argv before the clap-compatible parser sees it
+    int gpus = 1;
+    {
+        int w = 1;
+        for (int i = 1; i < argc; ++i) {
+            const bool eq = !std::strncmp(argv[i], "--gpus=", 7);
+            if (eq || (!std::strcmp(argv[i], "--gpus") && i + 1 < argc)) {
+                const char *v = eq ? argv[i] + 7 : argv[++i];
+                gpus = !std::strcmp(v, "all") ? 0 : std::atoi(v);
+                if (gpus < 0) gpus = 1;
+                continue;
+            }
+            argv[w++] = argv[i];
+        }
+        argc = w;
+    }
     rgh_cli_options opt;
     if (rgh_cli_parse(argc, argv, &opt) != RGH_OK) {
         std::fprintf(stderr, "error: %s\n\n%s", rgh_last_error(), kUsage);
@@ -87,20 +106,43 @@ int main(int argc, char **argv) {
 
     const char *dev_env = std::getenv("RAINGUN_DEVICE");
     rg_scene *scene = nullptr;
-    if (rg_scene_create(rgh_scene_desc(hs), dev_env ? std::atoi(dev_env) : 0, &scene) != RG_OK)
-        die("Could not upload the scene", rg_last_error(), 101);
+    int create_rc;
+    if (gpus == 1) {
+        create_rc = rg_scene_create(rgh_scene_desc(hs), dev_env ? std::atoi(dev_env) : 0, &scene);
+    } else {
+        const int have = rg_device_count();
+        if (gpus == 0 || gpus > have) gpus = have;
+        std::vector<int32_t> devices;
+        for (int k = 0; k < gpus; ++k) devices.push_back(k);
+        create_rc = gpus > 0 ? rg_scene_create_multi(rgh_scene_desc(hs), devices.data(), (uint32_t)devices.size(), &scene)
+                             : rg_scene_create(rgh_scene_desc(hs), 0, &scene);   // no device: fails with the library's message
+    }
+    if (create_rc != RG_OK) die("Could not upload the scene", rg_last_error(), 101);
 
     std::vector<uint8_t> image((size_t)opt.width * opt.height * 4);
     const auto t0 = std::chrono::steady_clock::now();
     int rc;
+    rg_stats stats;
+    std::memset(&stats, 0, sizeof stats);
     if (opt.preview) {
         Collector c{&image, opt.width, opt.height, 0};
-        rc = rg_render_stream(scene, opt.width, opt.height, 0, collect_rows, &c, nullptr);
+        rc = rg_render_stream(scene, opt.width, opt.height, 0, collect_rows, &c, &stats);
     } else {
-        rc = rg_render(scene, opt.width, opt.height, image.data(), nullptr);
+        rc = rg_render(scene, opt.width, opt.height, image.data(), &stats);
     }
     const auto t1 = std::chrono::steady_clock::now();
     if (rc != RG_OK) die("render failed", rg_last_error(), 101);
+    // Where the reference panics, it writes no image and exits 101; the device counts those pixels instead of
+    // unwinding, so the decision is taken here: NaN hit distance (scene.rs:38), `.unwrap()` on a transmission
+    // that does not exist (rendering.rs:106), an AABB hit no face claims (bodies.rs:324).
+    if (stats.err_nan_distance || stats.err_transmission_none || stats.err_aabb_normal) {
+        std::fprintf(stderr,
+                     "raingun: the reference would have panicked on this scene: %llu NaN hit distance(s) (scene.rs:38), %llu missing "
+                     "transmission(s) (rendering.rs:106), %llu undecidable box normal(s) (bodies.rs:324); no image written\n",
+                     (unsigned long long)stats.err_nan_distance, (unsigned long long)stats.err_transmission_none,
+                     (unsigned long long)stats.err_aabb_normal);
+        return 101;
+    }
     if (rgh_png_save(opt.output, image.data(), opt.width, opt.height, 4) != RGH_OK) die(rgh_last_error(), nullptr, 101);
     const auto t2 = std::chrono::steady_clock::now();
     using ms = std::chrono::milliseconds;

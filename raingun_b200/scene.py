@@ -104,6 +104,8 @@ class Stats(ctypes.Structure):
         ("grid_refills", ctypes.c_uint64),
         ("grid_lane_steps", ctypes.c_uint64),
         ("grid_lane_slots", ctypes.c_uint64),
+        ("pipeline_used", ctypes.c_uint32),
+        ("devices_used", ctypes.c_uint32),
     ]
 
     @property

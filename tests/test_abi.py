@@ -37,7 +37,7 @@ def test_struct_layouts_match_header():
     assert SceneDesc.n_bodies.offset == 28 and SceneDesc.body_kind.offset == 32
     assert SceneDesc.n_lights.offset == 104 and SceneDesc.light_kind.offset == 112
     assert SceneDesc.textures.offset == 144 and ctypes.sizeof(SceneDesc) == 152
-    assert ctypes.sizeof(Stats) == 176
+    assert ctypes.sizeof(Stats) == 184
 
 
 def test_validation_without_device():
@@ -100,7 +100,7 @@ def test_headers_are_plain_c(tmp_path):
         "    rg_scene_desc d; rg_stats s; rgh_image im; rgh_cli_options o; rg_scene *sc = 0; rgh_scene *hs = 0;\n"
         "    (void)d; (void)s; (void)im; (void)o;\n"
         "    /* take the address of every entry point a host would bind */\n"
-        "    void *fns[] = {(void *)rg_scene_create, (void *)rg_scene_destroy, (void *)rg_scene_set_option, (void *)rg_render,\n"
+        "    void *fns[] = {(void *)rg_scene_create, (void *)rg_scene_create_multi, (void *)rg_scene_device_count, (void *)rg_scene_destroy, (void *)rg_scene_set_option, (void *)rg_render,\n"
         "                   (void *)rg_render_rows, (void *)rg_render_rows_device, (void *)rg_render_rowlist_device,\n"
         "                   (void *)rg_render_rowlist_scatter, (void *)rg_shared_frame_create, (void *)rg_shared_frame_open,\n"
         "                   (void *)rg_shared_frame_close, (void *)rg_render_stream, (void *)rg_last_error, (void *)rg_device_count,\n"

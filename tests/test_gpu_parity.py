@@ -104,6 +104,7 @@ def test_host_free_loop_graph_replay_and_host_sized_loop_agree(oracle):
                              ("test1", example_scene("test1"), 200, 150)):
         ref, ost, _ = oracle.render(data, w, h)
         with rg.Scene(data) as sc:
+            sc.set_pipeline(rg.PIPELINE_WAVEFRONT)   # (the default would pick the megakernel for test1's handful of bodies)
             for it in range(4):
                 img = sc.render_image(w, h)
                 st = sc.last_stats
@@ -147,6 +148,69 @@ def test_host_free_queue_overflow_falls_back_to_exact_queues(oracle):
             img = sc.render_image(w, h)
             _assert_same(img, ref, sc.last_stats, ost, f"overflow frame {it}")
             assert sc.last_stats.host_free == 0
+
+
+def test_multi_device_scene_renders_the_single_device_frame(oracle):
+    """Multi-GPU inside the library (rg_scene_create_multi / RG_DEVICE_ALL; rayon's par_iter, rendering.rs:27-35):
+    one thread per device, row tiles owned statically or claimed from the atomic tile counter, every device
+    copying its rows into the caller's buffer.  On a one-GPU box the same machinery runs as several lanes
+    of device 0; with more GPUs it spans them.  Bytes and ray counts must equal the single-device render."""
+    ndev = rg.device_count()
+    layouts = [[0, 0, 0]] + ([list(range(ndev))] if ndev > 1 else [])
+    for name, data, w, h in (("C4-small", make_scene("C4", spheres=400, depth=6)[0], 256, 147),
+                             ("test3", example_scene("test3"), 200, 150)):
+        ref, ost, _ = oracle.render(data, w, h)
+        for devices in layouts:
+            with rg.Scene(data, devices=devices) as sc:
+                assert sc.device_count == len(devices)
+                for schedule, tile_rows in ((1, 8), (2, 8), (2, 3), (0, 16)):
+                    sc.set_option(rg._native.OPT_SCHEDULE, schedule)
+                    sc.set_option(rg._native.OPT_TILE_ROWS, tile_rows)
+                    img = sc.render_image(w, h)
+                    _assert_same(img, ref, sc.last_stats, ost, f"{name}/{devices}/schedule {schedule}/tiles {tile_rows}")
+                    assert 1 <= sc.last_stats.devices_used <= len(devices)
+                band = sc.render_rows(w, h, 13, 101)
+                assert np.array_equal(band, ref[13:101])
+                got = np.zeros_like(ref)
+                assert sc.streaming_render(w, h, lambda y0, rows: got.__setitem__(slice(y0, y0 + rows.shape[0]), rows) or True,
+                                           band_rows=40) is True
+                assert np.array_equal(got, ref)
+                import torch
+                with pytest.raises(rg.RaingunError) as e:   # device-pointer entry points need one device
+                    sc.render_rows_device(w, h, 0, h, torch.empty(w * h * 4, dtype=torch.uint8, device="cuda").data_ptr(), 0)
+                assert e.value.code == rg._native.E_INVALID
+    with rg.Scene(example_scene("test2"), device=rg.DEVICE_ALL) as sc:   # every visible GPU
+        assert sc.device_count == ndev
+        ref, _, _ = oracle.render(example_scene("test2"), 160, 120)
+        assert np.array_equal(sc.render_image(160, 120), ref)
+
+
+def test_concurrent_render_on_one_handle_is_refused():
+    """The reference's &Scene is Sync; a device scene owns its scratch queues, so a second render on a busy
+    handle returns RG_E_BUSY instead of racing (one handle per thread is the supported way)."""
+    import threading
+
+    data, _ = make_scene("C3", spheres=600, depth=4)
+    w, h = 1920, 1080
+    with rg.Scene(data) as sc:
+        ref = sc.render_image(w, h)
+        results = []
+
+        def work():
+            try:
+                results.append(("ok", sc.render_image(w, h)))
+            except rg.RaingunError as e:
+                results.append(("err", e.code))
+
+        for _ in range(6):
+            ts = [threading.Thread(target=work) for _ in range(3)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+        assert all(kind == "ok" and np.array_equal(val, ref) or kind == "err" and val == rg._native.E_BUSY for kind, val in results)
+        assert any(kind == "ok" for kind, _ in results)
+        assert np.array_equal(sc.render_image(w, h), ref)   # the handle is usable afterwards
 
 
 def test_depth_limit_like_draft(oracle):
