@@ -218,6 +218,108 @@ def run_reference(args, rank):
     return 0
 
 
+def profiled_thread_instructions():
+    """Thread instructions k_trace_grid executes per ray, from the newest committed ncu capture
+    (profiles/r*_grid_counters.json: smsp__thread_inst_executed.sum and the rays of the captured launches);
+    None when absent.  ncu cannot run inside the bench, so this one factor of the issue roofline is a
+    profile constant of the same code on the same workload; everything else is measured in this run."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_grid_counters.json")), reverse=True):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            return float(d["thread_inst_per_ray"]), os.path.basename(path), d
+        except (OSError, ValueError, KeyError):
+            continue
+    return None, None, None
+
+
+def grid_issue_roofline(rg, _native, data, w, h, staging, sptr, local_rank, value_mrays, clocks):
+    """k_trace_grid does no dense arithmetic and moves ~0.2 TB/s: neither the FP32 pipe nor HBM bounds it.  What
+    bounds a divergent traversal is the chip's LANE-ISSUE rate: 148 SMs x 4 schedulers x 32 lanes x clock
+    thread-instructions per second.  achieved = thread instructions per ray (ncu, committed profile) x rays/s
+    (this run); frac = IPC/4 x active lanes/32.  The per-ray walk counters come from one instrumented frame."""
+    sc = rg.Scene(data, device=local_rank)
+    sc.set_option(_native.OPT_TRACE_STATS, 1)
+    st = sc.render_rows_device(w, h, 0, h, staging.data_ptr(), sptr)
+    sc.close()
+    r = max(1, st.rays)
+    tipr, src, prof = profiled_thread_instructions()
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    peak = 148 * 4 * 32 * sm_mhz * 1e6
+    out = {"bound": "lane-issue slots (148 SM x 4 schedulers x 32 lanes x SM clock)", "peak": peak / 1e12, "unit": "T thread-instr/s",
+           "sm_mhz_used": sm_mhz,
+           "per_ray": {"cells_visited": st.grid_cells / r, "records_fetched_nonempty": st.grid_fetches / r, "cull_tests": st.grid_culls / r,
+                       "exact_fp64_tests": st.exact_tests / r, "rays_per_refill": r / max(1, st.grid_refills),
+                       "scan_lane_use": st.grid_lane_steps / max(1, st.grid_lane_slots),
+                       "l2_bytes_algorithmic": 48.0 * st.grid_cells / r + 48.0 + 12.0},
+           "per_ray_note": "l2_bytes_algorithmic = 48 B per cell visited (chained records of crowded cells add a few per cent) "
+                           "+ 48 B ray + 12 B hit"}
+    if tipr:
+        achieved = tipr * value_mrays * 1e6
+        out.update({"achieved": achieved / 1e12, "frac": achieved / peak, "thread_instr_per_ray": tipr, "thread_instr_source": f"profiles/{src}",
+                    "ipc_over_4_times_lanes_over_32": (prof or {}).get("ipc_lanes_product")})
+    return out
+
+
+def run_configs(rg, _native, torch, device, local_rank, world, sha):
+    """BASELINE.json configs beside the headline one: the three shipped scenes at their native 800x600 (configs[0..1];
+    test1 also on the CPU oracle, full frame), C3 at 4K on one GPU (configs[2]) and C5 at 8K (configs[4]) — on one GPU
+    and, at N > 1, row-tile sharded over all N GPUs inside the library.  Device-resident ms/frame (CUDA events),
+    best of a few frames after a warm-up."""
+    from oracle import oracle
+    from raingun_b200.examples import bundled_texture_loader, example_scene
+    from raingun_b200.synth import make_scene
+    out = {}
+    buf = torch.empty(7680 * 4320 * 4, dtype=torch.uint8, device=device)
+    stream = torch.cuda.current_stream(device).cuda_stream
+
+    def timed(sc, w_, h_, reps):
+        best, st_ = 1e30, None
+        for _ in range(reps):
+            st_ = sc.render_rows_device(w_, h_, 0, h_, buf.data_ptr(), stream)
+            best = min(best, st_.ms_device)
+        return best, st_
+
+    for name in ("test1", "test2", "test3"):
+        sd = example_scene(name)
+        with rg.Scene(sd, device=local_rank) as sc:
+            ms, st_ = timed(sc, 800, 600, 6)
+        entry = {"width": 800, "height": 600, "ms_per_frame": ms, "mrays_per_s": st_.rays / ms / 1e3, "rays": int(st_.rays),
+                 "pipeline": {0: "wavefront", 1: "megakernel"}.get(st_.pipeline_used, "?"), "launches": int(st_.gpu_launches)}
+        if name == "test1":   # BASELINE.json configs[0]: the reference CLI's own CPU case, here the oracle on all host threads
+            O = oracle()
+            t0 = time.perf_counter()
+            ref, ost, _ = O.render(sd, 800, 600)
+            dt = time.perf_counter() - t0
+            img = buf[: 800 * 600 * 4].view(600, 800, 4).cpu().numpy()
+            entry["cpu_oracle"] = {"ms_per_frame": dt * 1e3, "mrays_per_s": ost.rays / dt / 1e6, "threads": O.hardware_threads(),
+                                   "identical_to_gpu_frame": bool(np.array_equal(ref, img))}
+        out[f"{name}@800x600"] = entry
+    for wl in ("C3", "C5"):
+        sd, spec_ = make_scene(wl, texture_loader=bundled_texture_loader)
+        with rg.Scene(sd, device=local_rank) as sc:
+            ms, st_ = timed(sc, spec_.width, spec_.height, 4 if wl == "C3" else 2)
+        single_sha = sha(buf[: spec_.width * spec_.height * 4].cpu().numpy())
+        entry = {"width": spec_.width, "height": spec_.height, "bodies": int(sd.n_bodies), "ms_per_frame": ms,
+                 "mrays_per_s": st_.rays / ms / 1e3, "rays": int(st_.rays), "batches": int(st_.batches), "n_gpus": 1}
+        if wl == "C5" and world > 1 and rg.device_count() >= world:
+            host = torch.empty((spec_.height, spec_.width, 4), dtype=torch.uint8).pin_memory()
+            with rg.Scene(sd, devices=list(range(world))) as msc:
+                best = 1e30
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    mst = msc.render_rows_into(spec_.width, spec_.height, 0, spec_.height, host.data_ptr())
+                    best = min(best, (time.perf_counter() - t0) * 1e3)
+            entry["sharded"] = {"n_gpus": world, "ms_per_frame_wall_incl_d2h": best, "mrays_per_s": mst.rays / best / 1e3,
+                                "identical_to_one_gpu_frame": sha(host.numpy()) == single_sha,
+                                "how": "row tiles across the GPUs inside the library (rg_scene_create_multi), frame delivered to pinned host memory"}
+            del host
+        out[f"{wl}@{spec_.width}x{spec_.height}"] = entry
+    del buf
+    return out
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def main() -> int:
     ap = argparse.ArgumentParser()
@@ -231,6 +333,11 @@ def main() -> int:
     ap.add_argument("--tile-rows", type=int, default=8)
     ap.add_argument("--gather", default="peer", choices=["peer", "reduce", "p2p"],
                     help="N>1: peer = rows stored straight into rank 0's frame over NVLink by the last kernel (CUDA IPC)")
+    ap.add_argument("--e2e-gather", default="host", choices=["host", "device"],
+                    help="N>1 end-to-end arm: host = every rank copies its rows over its own PCIe link into ONE pinned "
+                         "shared-memory frame; device = gather on rank 0's GPU (--gather) and one D2H from there")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config table (test1/2/3, C3, C5)")
+    ap.add_argument("--no-in-library", action="store_true", help="skip the in-library multi-GPU arm (N>1)")
     ap.add_argument("--lead", type=float, default=0.6, help="share of a rank's static tiles given to its first in-flight batch")
     ap.add_argument("--inflight", type=int, default=1,
                     help="N>1: wavefront batches each rank keeps in flight (scene handle + stream + host thread each)")
@@ -395,7 +502,32 @@ def main() -> int:
     for sc_, _ in lanes:
         sc_.close()
 
+    import hashlib
+
+    def sha(arr) -> str:
+        return hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest()
+
+    # the frame of the device-resident arm, for the equality check of all arms below
+    value_frame_sha = None
+    if rank == 0:
+        value_frame_sha = sha((gathered["frame"] if world > 1 else staging.view(h, w, 4)).cpu().numpy())
+
     upload_s = [0.0]
+    host_frames = None
+    e2e_gather = args.e2e_gather if world > 1 else "single"
+    if world > 1 and args.e2e_gather == "host":
+        from raingun_b200.dist import SharedHostFrame
+        try:
+            host_frames = SharedHostFrame(w, h, rank, world, tag="e2e")
+        except Exception as e:   # /dev/shm or pinning unavailable: every rank falls back together
+            print(f"[bench] shared host frame unavailable on rank {rank}: {e}", file=sys.stderr, flush=True)
+        ok = torch.tensor([0 if host_frames is None else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if host_frames is not None:
+                host_frames.close()
+                host_frames = None
+            e2e_gather = "device"
 
     def step_e2e():
         t_up = time.perf_counter()
@@ -404,6 +536,15 @@ def main() -> int:
         upload_s[0] += time.perf_counter() - t_up   # reported separately as well
         if world == 1:
             r = sc.render_rows_into(w, h, 0, h, host_frame.data_ptr()).rays
+            sc.close()
+        elif host_frames is not None:
+            # every rank delivers its own rows over its own PCIe link into the one pinned host frame
+            frame_counter[0] += 1
+            res = render_frame_sharded(
+                [lambda rows, fptr, sc_=sc: sc_.render_rowlist_host(w, h, rows, fptr)], w, h, rank, world, frame_counter[0], device,
+                tile_rows=args.tile_rows, schedule=args.schedule, gather_mode="host", peer_frames=host_frames)
+            gathered["host_frame"] = res.frame
+            r = sum(s_.rays for s_ in res.stats)
             sc.close()
         else:
             ls = make_lanes(sc)            # every lane re-uploads the scene (counted in h2d_bytes_per_step)
@@ -426,7 +567,42 @@ def main() -> int:
     e2e_s = reduce_max(time.perf_counter() - t0)
     (e2e_rays,) = reduce_sum([e2e_rays])
     e2e_value = e2e_rays / e2e_s / 1e6 if e2e_s > 0 else 0.0
-    checksum = int(host_frame.view(-1)[:: 4099].to(torch.int64).sum().item()) if rank == 0 else 0
+    e2e_frame_sha = None
+    if rank == 0:
+        e2e_frame_sha = sha(gathered["host_frame"].numpy() if host_frames is not None else host_frame.numpy())
+        if e2e_frame_sha != value_frame_sha:
+            print(json.dumps({"error": "the end-to-end frame differs from the device-resident frame",
+                              "value_frame_sha256": value_frame_sha, "e2e_frame_sha256": e2e_frame_sha}), flush=True)
+            return 3
+    if host_frames is not None:
+        host_frames.close()
+
+    # ---- the same frame rendered on all N GPUs INSIDE the library (rank 0 only; the other ranks idle at the
+    # barrier): rg_scene_create_multi + rg_render — what a host without torchrun gets (rendering.rs:27-35)
+    in_library = None
+    if world > 1 and not args.no_in_library:
+        barrier()
+        if rank == 0 and rg.device_count() >= world:
+            in_library = {}
+            for label, schedule in (("static", 1), ("steal", 2)):
+                with rg.Scene(data, devices=list(range(world))) as msc:
+                    msc.set_accel(accel)
+                    msc.set_option(_native.OPT_SCHEDULE, schedule)
+                    for _ in range(max(2, min(args.warmup, 3))):
+                        msc.render_rows_into(w, h, 0, h, host_frame.data_ptr())
+                    t0 = time.perf_counter()
+                    mrays = 0
+                    for _ in range(args.steps):
+                        mrays += msc.render_rows_into(w, h, 0, h, host_frame.data_ptr()).rays
+                    dt = time.perf_counter() - t0
+                    st_ = msc.last_stats
+                    in_library[label] = {"ms_per_frame": dt / max(1, args.steps) * 1e3, "value": mrays / dt / 1e6, "unit": UNIT,
+                                         "devices_used": int(st_.devices_used), "batches_last_frame": int(st_.batches),
+                                         "frame_sha256_equal": sha(host_frame.numpy()) == value_frame_sha}
+            in_library["what"] = ("one process, one library thread per GPU, row tiles owned statically (static) or a 1/16 tail claimed "
+                                  "from a std::atomic counter (steal); scene already uploaded; timed: rg_render into pinned host memory, "
+                                  "every GPU copying its rows over its own PCIe link (wall clock)")
+        barrier()
 
     # ---- roofline arm (rank 0): the reference algorithm itself — brute force, every ray x every
     # body — whose dominant kernel k_trace_brute is FP32-pipe bound.
@@ -467,10 +643,25 @@ def main() -> int:
                                        "has no FP32 figure; nominal 74.4 TFLOP/s at 1965 MHz)",
                         "fp64_peak_tflops": fp64_peak,
                         "fp64_fallthrough_frac": bexact / btests if btests else None,   # pairs the FP32 cull could not reject
+                        # the 17 algorithmic flop of a pair are executed as 7 FFMA (14 flop) + compare: the FMA pipe's own utilisation
+                        "executed_ffma_frac": (brays * float(data.n_bodies) * 14.0 / (tr_ms * 1e-3) / 1e12) / fp32_peak,
                         "share_of_step": tr_ms / dev_ms if dev_ms > 0 else None}
             brute = {"value": brays / (dev_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": dev_ms / bsteps,
                      "ms_trace_kernels": tr_ms / bsteps, "steps": bsteps}
         barrier()
+
+    # ---- every BASELINE.json config in the one run (rank 0; the other ranks idle at the barrier) ----------
+    configs = None
+    if not args.no_configs:
+        barrier()
+        if rank == 0:
+            configs = run_configs(rg, _native, torch, device, local_rank, world, sha)
+        barrier()
+
+    # ---- the kernel behind `value` (k_trace_grid) against ITS ceiling: lane-issue slots -------------------
+    grid_roofline = None
+    if rank == 0 and accel_used == "grid":
+        grid_roofline = grid_issue_roofline(rg, _native, data, w, h, staging, sptr, local_rank, value, clocks)
 
     # ---- CPU baseline beside it (rank 0, N = 1): the oracle on all host threads, bounded sample
     cpu_baseline = None
@@ -497,15 +688,19 @@ def main() -> int:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": desc_bytes * world * inflight,
                     "d2h_bytes_per_step": h * w * 4, "ms_per_step": e2e_s / max(1, args.steps) * 1e3,
                     "scene_upload_ms_per_step": upload_s[0] / max(1, args.steps) * 1e3,
-                    "what": "rg_scene_create (scene H2D) + render + RGBA8 frame D2H into pinned host memory + rg_scene_destroy, per step"},
+                    "gather": e2e_gather,
+                    "what": "rg_scene_create (scene H2D) + render + RGBA8 frame D2H into pinned host memory + rg_scene_destroy, per step"
+                            + ("; N>1: every rank copies its rows into ONE pinned shared-memory frame over its own PCIe link" if e2e_gather == "host" else "")},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "brute_force": brute,
             # the kernel that dominates the `value` arm is latency / issue bound, not FP32- or HBM-bound: its
             # figure of merit is rays/s; the ncu numbers that say so come from the committed capture
             "value_arm_kernel": {"kernel": "k_trace_grid (exact grid traversal, nearest + any-hit)", "bound": "latency/issue",
                                  "trace_ms_per_step_sum_of_spans": (last_stats.ms_trace if last_stats else None),
                                  "device_ms_last_step": (last_stats.ms_device if last_stats else None),
-                                 "rays_per_s": value * 1e6, "ncu": profiled_grid_kernel()},
-            "cpu_baseline": cpu_baseline, "frame_checksum": checksum,
+                                 "rays_per_s": value * 1e6, "roofline": grid_roofline, "ncu": profiled_grid_kernel()},
+            "cpu_baseline": cpu_baseline, "frame_sha256": value_frame_sha,
+            "frame_sha256_equal_across_arms": True,   # device-resident, end-to-end (and gathered, N > 1) frames: checked above
+            "in_library_multi_gpu": in_library, "configs": configs,
         }
         print(json.dumps(line), flush=True)
     if peer_frames is not None:

@@ -245,6 +245,24 @@ int rg_render_rowlist_scatter(rg_scene *scene, uint32_t width, uint32_t height,
                               const uint32_t *rows, uint32_t n_rows, void *d_frame,
                               void *cuda_stream, rg_stats *stats);
 
+/* Row-tile sharding with the frame in HOST memory: renders the listed image rows on the scene's device and
+ * copies row rows[k] to `frame + rows[k]*width*4` (`frame` = address of image row 0 of a full
+ * width*height*4 frame; runs of adjacent rows travel as one copy, an interleaved share as one strided
+ * copy).  With one process (or thread) per GPU and `frame` a pinned buffer all of them see — the caller's
+ * own, or a shared-memory file registered with rg_host_register in every process — every GPU delivers its
+ * rows over its own PCIe link and nothing is gathered on a GPU first. */
+int rg_render_rowlist_host(rg_scene *scene, uint32_t width, uint32_t height,
+                           const uint32_t *rows, uint32_t n_rows, uint8_t *frame, rg_stats *stats);
+/* Pins caller-owned host memory (cudaHostRegister, portable) so that device-to-host copies into it run at
+ * full PCIe speed; undo with rg_host_unregister before freeing it. */
+int rg_host_register(void *ptr, size_t bytes);
+int rg_host_unregister(void *ptr);
+
+/* One process driving several GPUs: lets kernels running on `device` store into memory that lives on `peer`
+ * (cudaDeviceEnablePeerAccess; NVLink / NVSwitch on a B200 box), so that rg_render_rowlist_scatter on one GPU
+ * can write its rows into a frame on another.  Harmless if already enabled. */
+int rg_device_enable_peer(int32_t device, int32_t peer);
+
 /* A device frame that other PROCESSES (one per GPU) can map: create on the owning rank, pass the
  * opaque handle bytes to the others (any channel), open there.  Close with is_owner = 1 on the
  * creating rank (frees the memory), 0 elsewhere (unmaps). */
@@ -259,6 +277,23 @@ int rg_shared_frame_close(int32_t device, void *d_ptr, int32_t is_owner);
  * non-zero. */
 int rg_render_stream(rg_scene *scene, uint32_t width, uint32_t height,
                      uint32_t band_rows, rg_rows_cb cb, void *user, rg_stats *stats);
+
+/* Destroying a scene parks its device-side context (scratch queues of possibly several GB, frame, arena,
+ * stream, pinned buffers) for the next scene created on the same device, so that a host that re-uploads
+ * the scene every frame never pays cudaMalloc again.  rg_trim releases everything parked (on all devices)
+ * and returns the number of contexts freed; the library also does so itself before reporting RG_E_NOMEM. */
+int rg_trim(void);
+
+/* Unquantised output.  `RenderedPixel.color` is an f32 `Color` (rendering.rs:18-22,59-65): streaming_render's
+ * consumers receive the colour BEFORE `Color::rgba` (color.rs:32-37) narrows it to bytes.  These two entry
+ * points deliver exactly that — 3 floats (r, g, b) per pixel, row-major, bit-identical to the reference's
+ * f32 values — for hosts whose consumer is not the CLI's RGBA8 collector.  Single-device scenes. */
+typedef int (*rg_rows_f32_cb)(uint32_t y0, uint32_t rows, uint32_t width,
+                              const float *rgb, void *user);
+int rg_render_rows_f32(rg_scene *scene, uint32_t width, uint32_t height,
+                       uint32_t y0, uint32_t y1, float *rgb_out, rg_stats *stats);
+int rg_render_stream_f32(rg_scene *scene, uint32_t width, uint32_t height,
+                         uint32_t band_rows, rg_rows_f32_cb cb, void *user, rg_stats *stats);
 
 /* Thread-local description of the last failure in this thread. */
 const char *rg_last_error(void);

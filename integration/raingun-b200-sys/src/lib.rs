@@ -117,6 +117,9 @@ pub enum rg_scene {}
 pub type rg_rows_cb =
     extern "C" fn(y0: u32, rows: u32, width: u32, rgba: *const u8, user: *mut c_void) -> c_int;
 
+pub type rg_rows_f32_cb =
+    extern "C" fn(y0: u32, rows: u32, width: u32, rgb: *const f32, user: *mut c_void) -> c_int;
+
 extern "C" {
     pub fn rg_scene_create(desc: *const rg_scene_desc, device: i32, out: *mut *mut rg_scene) -> c_int;
     pub fn rg_scene_create_multi(desc: *const rg_scene_desc, devices: *const i32, n_devices: u32,
@@ -137,11 +140,21 @@ extern "C" {
     pub fn rg_render_rowlist_scatter(scene: *mut rg_scene, width: u32, height: u32, rows: *const u32,
                                      n_rows: u32, d_frame: *mut c_void, cuda_stream: *mut c_void,
                                      stats: *mut rg_stats) -> c_int;
+    pub fn rg_render_rowlist_host(scene: *mut rg_scene, width: u32, height: u32, rows: *const u32, n_rows: u32,
+                                  frame: *mut u8, stats: *mut rg_stats) -> c_int;
+    pub fn rg_host_register(ptr: *mut c_void, bytes: usize) -> c_int;
+    pub fn rg_host_unregister(ptr: *mut c_void) -> c_int;
+    pub fn rg_device_enable_peer(device: i32, peer: i32) -> c_int;
     pub fn rg_shared_frame_create(device: i32, bytes: usize, d_ptr: *mut *mut c_void, handle: *mut u8) -> c_int;
     pub fn rg_shared_frame_open(device: i32, handle: *const u8, d_ptr: *mut *mut c_void) -> c_int;
     pub fn rg_shared_frame_close(device: i32, d_ptr: *mut c_void, is_owner: i32) -> c_int;
     pub fn rg_render_stream(scene: *mut rg_scene, width: u32, height: u32, band_rows: u32,
                             cb: rg_rows_cb, user: *mut c_void, stats: *mut rg_stats) -> c_int;
+    pub fn rg_render_rows_f32(scene: *mut rg_scene, width: u32, height: u32, y0: u32, y1: u32,
+                              rgb_out: *mut f32, stats: *mut rg_stats) -> c_int;
+    pub fn rg_render_stream_f32(scene: *mut rg_scene, width: u32, height: u32, band_rows: u32,
+                                cb: rg_rows_f32_cb, user: *mut c_void, stats: *mut rg_stats) -> c_int;
+    pub fn rg_trim() -> c_int;
     pub fn rg_last_error() -> *const c_char;
     pub fn rg_measure_peaks(device: i32, fp32_tflops: *mut f64, fp64_tflops: *mut f64,
                             sm_clock_mhz: *mut f64) -> c_int;

@@ -23,7 +23,7 @@ from ._native import (ACCEL_AUTO, ACCEL_BRUTE, ACCEL_GRID, DEVICE_ALL, PIPELINE_
                       RaingunError)
 from .scene import SceneData, SceneError, Stats, load_scene, parse_scene, scene_from_dict
 
-__all__ = ["Scene", "SharedFrame", "SceneData", "SceneError", "RaingunError", "Stats", "load_scene", "parse_scene",
+__all__ = ["Scene", "SharedFrame", "host_register", "host_unregister", "trim", "SceneData", "SceneError", "RaingunError", "Stats", "load_scene", "parse_scene",
            "scene_from_dict", "device_count", "measure_peaks", "ACCEL_AUTO", "ACCEL_BRUTE", "ACCEL_GRID",
            "PIPELINE_WAVEFRONT", "PIPELINE_MEGAKERNEL", "PIPELINE_AUTO", "DEVICE_ALL"]
 
@@ -37,6 +37,20 @@ def measure_peaks(device: int = 0):
     a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
     _native.check(_native.lib().rg_measure_peaks(device, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
     return a.value, b.value, c.value
+
+
+def trim() -> int:
+    """Frees the device-side contexts destroyed scenes have parked for reuse (rg_trim); returns how many."""
+    return int(_native.lib().rg_trim())
+
+
+def host_register(ptr: int, nbytes: int) -> None:
+    """Pins host memory for full-speed device-to-host copies (rg_host_register)."""
+    _native.check(_native.lib().rg_host_register(ctypes.c_void_p(ptr), nbytes))
+
+
+def host_unregister(ptr: int) -> None:
+    _native.check(_native.lib().rg_host_unregister(ctypes.c_void_p(ptr)))
 
 
 class SharedFrame:
@@ -190,6 +204,49 @@ class Scene:
         _native.check(_native.lib().rg_render_rowlist_scatter(
             self._h, width, height, ctypes.c_void_p(rows.ctypes.data), int(rows.size), ctypes.c_void_p(frame_ptr),
             ctypes.c_void_p(cuda_stream), ctypes.byref(st)))
+        self.last_stats = st
+        return st
+
+    def render_rows_f32(self, width: int, height: int, y0: int = 0, y1: Optional[int] = None) -> np.ndarray:
+        """The unquantised f32 colours (``RenderedPixel.color``, rendering.rs:18-22): (rows, width, 3) float32."""
+        y1 = height if y1 is None else y1
+        out = np.empty((max(0, y1 - y0), width, 3), np.float32)
+        st = Stats()
+        _native.check(_native.lib().rg_render_rows_f32(self._h, width, height, y0, y1, out.ctypes.data, ctypes.byref(st)))
+        self.last_stats = st
+        return out
+
+    def streaming_render_f32(self, width: int, height: int, on_rows: Callable[[int, np.ndarray], bool], band_rows: int = 0) -> bool:
+        """``streaming_render`` with the colours as the reference's channel carries them: unquantised f32 RGB."""
+        failure = []
+
+        def trampoline(y0, rows, w, ptr, _user):
+            try:
+                arr = np.ctypeslib.as_array(ptr, shape=(rows, w, 3))
+                keep_going = on_rows(int(y0), arr)
+                return 0 if (keep_going is None or keep_going) else 1
+            except BaseException as e:  # never unwind through C
+                failure.append(e)
+                return 1
+
+        cb = _native.ROWS_F32_CB(trampoline)
+        st = Stats()
+        rc = _native.lib().rg_render_stream_f32(self._h, width, height, band_rows, cb, None, ctypes.byref(st))
+        self.last_stats = st
+        if failure:
+            raise failure[0]
+        if rc == _native.E_CANCELLED:
+            return False
+        _native.check(rc)
+        return True
+
+    def render_rowlist_host(self, width: int, height: int, rows, frame_ptr: int) -> Stats:
+        """Renders the listed image rows and copies row ``rows[k]`` to ``frame_ptr + rows[k]*width*4`` in HOST
+        memory (a full frame, ideally pinned / ``host_register``-ed; may be shared by one process per GPU)."""
+        rows = np.ascontiguousarray(rows, np.uint32)
+        st = Stats()
+        _native.check(_native.lib().rg_render_rowlist_host(
+            self._h, width, height, ctypes.c_void_p(rows.ctypes.data), int(rows.size), ctypes.c_void_p(frame_ptr), ctypes.byref(st)))
         self.last_stats = st
         return st
 

@@ -29,10 +29,13 @@ OPT_HOST_FREE, OPT_GRAPH, OPT_TRACE_STATS, OPT_REORDER, OPT_SCHEDULE, OPT_TILE_R
 ROWS_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                            ctypes.POINTER(ctypes.c_uint8), ctypes.c_void_p)
 
+ROWS_F32_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                               ctypes.POINTER(ctypes.c_float), ctypes.c_void_p)
+
 # every symbol include/raingun_b200.h declares
 EXPORTS = ("rg_scene_create", "rg_scene_create_multi", "rg_scene_device_count", "rg_scene_destroy", "rg_scene_set_option", "rg_render", "rg_render_rows",
-           "rg_render_rows_device", "rg_render_rowlist_device", "rg_render_rowlist_scatter", "rg_shared_frame_create",
-           "rg_shared_frame_open", "rg_shared_frame_close", "rg_render_stream", "rg_last_error", "rg_measure_peaks",
+           "rg_render_rows_device", "rg_render_rowlist_device", "rg_render_rowlist_scatter", "rg_render_rowlist_host", "rg_host_register", "rg_host_unregister", "rg_device_enable_peer", "rg_shared_frame_create",
+           "rg_shared_frame_open", "rg_shared_frame_close", "rg_render_stream", "rg_render_rows_f32", "rg_render_stream_f32", "rg_trim", "rg_last_error", "rg_measure_peaks",
            "rg_device_count")
 IPC_HANDLE_BYTES = 64
 
@@ -75,6 +78,14 @@ def lib() -> ctypes.CDLL:
     L.rg_render_rowlist_device.argtypes = [vp, u32, u32, vp, u32, vp, vp, ctypes.POINTER(Stats)]
     L.rg_render_rowlist_scatter.restype = ctypes.c_int
     L.rg_render_rowlist_scatter.argtypes = [vp, u32, u32, vp, u32, vp, vp, ctypes.POINTER(Stats)]
+    L.rg_render_rowlist_host.restype = ctypes.c_int
+    L.rg_render_rowlist_host.argtypes = [vp, u32, u32, vp, u32, vp, ctypes.POINTER(Stats)]
+    L.rg_host_register.restype = ctypes.c_int
+    L.rg_host_register.argtypes = [vp, ctypes.c_size_t]
+    L.rg_host_unregister.restype = ctypes.c_int
+    L.rg_host_unregister.argtypes = [vp]
+    L.rg_device_enable_peer.restype = ctypes.c_int
+    L.rg_device_enable_peer.argtypes = [i32, i32]
     L.rg_shared_frame_create.restype = ctypes.c_int
     L.rg_shared_frame_create.argtypes = [i32, ctypes.c_size_t, ctypes.POINTER(vp), ctypes.c_char_p]
     L.rg_shared_frame_open.restype = ctypes.c_int
@@ -83,6 +94,12 @@ def lib() -> ctypes.CDLL:
     L.rg_shared_frame_close.argtypes = [i32, vp, i32]
     L.rg_render_stream.restype = ctypes.c_int
     L.rg_render_stream.argtypes = [vp, u32, u32, u32, ROWS_CB, vp, ctypes.POINTER(Stats)]
+    L.rg_render_rows_f32.restype = ctypes.c_int
+    L.rg_render_rows_f32.argtypes = [vp, u32, u32, u32, u32, vp, ctypes.POINTER(Stats)]
+    L.rg_render_stream_f32.restype = ctypes.c_int
+    L.rg_render_stream_f32.argtypes = [vp, u32, u32, u32, ROWS_F32_CB, vp, ctypes.POINTER(Stats)]
+    L.rg_trim.restype = ctypes.c_int
+    L.rg_trim.argtypes = []
     L.rg_last_error.restype = ctypes.c_char_p
     L.rg_last_error.argtypes = []
     L.rg_measure_peaks.restype = ctypes.c_int

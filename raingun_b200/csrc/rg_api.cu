@@ -17,7 +17,7 @@
 
 namespace rg {
 
-constexpr uint32_t kMegaAutoBodies = 16;
+constexpr uint32_t kMegaAutoBodies = 24;   // measured crossover (C4-style scenes, 1080p and 4K): megakernel ahead up to 24 spheres, level at 32
 static thread_local std::string g_last_error;
 static double g_last_ffma2_tflops = 0.0, g_last_ffma_tflops = 0.0;   // rg_measure_peaks detail
 
@@ -39,6 +39,8 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
     return RG_E_CUDA;
 }
 
+static size_t trim_parked(int device);
+
 int DeviceBuffer::reserve(size_t bytes) {
     if (bytes <= cap) return RG_OK;
     if (ptr) { cudaFree(ptr); ptr = nullptr; cap = 0; }
@@ -48,6 +50,11 @@ int DeviceBuffer::reserve(size_t bytes) {
         cudaGetLastError();
         e = cudaMalloc(&ptr, bytes);
         want = bytes;
+    }
+    if (e != cudaSuccess) {   // scratch parked by earlier scenes of this device may be what is in the way
+        cudaGetLastError();
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && trim_parked(dev) > 0) e = cudaMalloc(&ptr, bytes);
     }
     if (e != cudaSuccess) { ptr = nullptr; return cuda_fail(e, "cudaMalloc(scratch)", __FILE__, __LINE__); }
     cap = want;
@@ -94,11 +101,45 @@ struct ParkedContext {
     DCounters *d_counters = nullptr, *h_counters = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint8_t *h_stage = nullptr;   // pinned staging of the scene upload
+    size_t h_stage_cap = 0;
 };
+static void free_parked(ParkedContext &p) {   // device of the context must be current
+    p.wf.release();
+    p.frame.release();
+    p.rowlist.release();
+    p.arena.release();
+    if (p.d_counters) cudaFree(p.d_counters);
+    if (p.h_counters) cudaFreeHost(p.h_counters);
+    if (p.h_stage) cudaFreeHost(p.h_stage);
+    for (auto &e : p.ev) if (e) cudaEventDestroy(e);
+    if (p.stream) cudaStreamDestroy(p.stream);
+}
 static std::mutex g_park_mutex;
 // a few per device: a multi-GPU host keeps several batches (scene handles) in flight per GPU
 static std::map<int, std::vector<ParkedContext>> g_parked;
 constexpr size_t kMaxParkedPerDevice = 4;
+
+// frees every context parked on `device` (-1: on all devices); returns how many were freed
+static size_t trim_parked(int device) {
+    std::vector<std::pair<int, ParkedContext>> victims;
+    {
+        std::lock_guard<std::mutex> lock(g_park_mutex);
+        for (auto &kv : g_parked) {
+            if (device >= 0 && kv.first != device) continue;
+            for (auto &p : kv.second) victims.emplace_back(kv.first, std::move(p));
+            kv.second.clear();
+        }
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto &v : victims) {
+        cudaSetDevice(v.first);
+        free_parked(v.second);
+    }
+    cudaSetDevice(cur);
+    return victims.size();
+}
 
 void *SceneArena::alloc(size_t bytes) {
     bytes = (bytes + 255) & ~(size_t)255;
@@ -229,6 +270,34 @@ static int create_textures(rg_scene *sc, const rg_scene_desc *d) {
     return upload(sc, host.data(), host.size(), &sc->ds.tex);
 }
 
+// FP32 cull records (rg_cull.h) of every sphere, computed where the sphere list already is.  The arithmetic is
+// the host builder's of round 1 operation for operation (FP64, no contraction: this file is compiled with
+// -fmad=false), so the records are the same bits; cull2 is the pair-interleaved copy for the packed FFMA2 kernel.
+__global__ void __launch_bounds__(256) k_cull_records(const double4 *__restrict__ sph, uint32_t n, uint32_t n_padded, double px, double py,
+                                                      double pz, float4 *cull4, float4 *cull2) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;   // (no early return: the pair exchange below needs whole warps)
+    const float kInf = __int_as_float(0x7f800000);
+    float4 rec = make_float4(0.f, 0.f, 0.f, kInf);   // padding: rejects everything
+    if (i < n) {
+        const double4 sp = sph[i];
+        const double cx = sp.x - px, cy = sp.y - py, cz = sp.z - pz, r = sp.w;
+        const double C2 = cx * cx + cy * cy + cz * cz, r2 = r * r;
+        if (C2 < kCullHuge && r2 < kCullHuge) {   // also false for NaN
+            const double K = (C2 - r2) - kCullU * (kCullSphereC2 * C2 + kCullSphereR2 * r2);
+            rec = make_float4((float)cx, (float)cy, (float)cz, (float)K);
+        } else {
+            rec = make_float4(0.f, 0.f, 0.f, -kInf);   // never rejected
+        }
+    }
+    // pair (2k, 2k+1) -> cull2[2k] = (x0, x1, y0, y1), cull2[2k+1] = (z0, z1, -K0, -K1)
+    const float ox = __shfl_xor_sync(0xffffffffu, rec.x, 1), oy = __shfl_xor_sync(0xffffffffu, rec.y, 1),
+                oz = __shfl_xor_sync(0xffffffffu, rec.z, 1), ow = __shfl_xor_sync(0xffffffffu, rec.w, 1);
+    if (i >= n_padded) return;
+    cull4[i] = rec;
+    if ((i & 1u) == 0) cull2[i] = make_float4(rec.x, ox, rec.y, oy);
+    else cull2[i] = make_float4(oz, rec.z, -ow, -rec.w);
+}
+
 static int build_scene(rg_scene *sc, const rg_scene_desc *d) {
     DScene &ds = sc->ds;
     const uint32_t n = d->n_bodies;
@@ -240,10 +309,37 @@ static int build_scene(rg_scene *sc, const rg_scene_desc *d) {
     ds.fov_adj = fov_adjustment(d->fov);
     for (int k = 0; k < 3; ++k) ds.default_color[k] = d->default_color[k];
 
-    std::vector<BodyMat> mats(n);
-    std::vector<double> sph;          // n_spheres x 4
-    std::vector<uint32_t> sph_body, misc_body;
-    for (uint32_t i = 0; i < n; ++i) {
+    uint32_t ns = 0;
+    for (uint32_t i = 0; i < n; ++i) ns += d->body_kind[i] == RG_BODY_SPHERE ? 1u : 0u;
+    const uint32_t nm = n - ns;
+    ds.n_spheres = ns;
+    ds.n_misc = nm;
+    const size_t cull_padded = ((size_t)ns + 3) / 4 * 4;
+
+    // ---- everything the device needs from the host, laid out in ONE pinned staging buffer -> one async copy
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t off_kind = 0, off_geom = align(off_kind + n), off_mat = align(off_geom + (size_t)n * 64),
+                 off_sph = align(off_mat + (size_t)n * sizeof(BodyMat)), off_sphb = align(off_sph + (size_t)ns * 32),
+                 off_misc = align(off_sphb + (size_t)ns * 4), total = align(off_misc + (size_t)nm * 4);
+    if (sc->h_stage_cap < total) {
+        if (sc->h_stage) cudaFreeHost(sc->h_stage);
+        sc->h_stage = nullptr;
+        sc->h_stage_cap = 0;
+        const size_t want = total + total / 4 + 4096;
+        RG_CUDA(cudaMallocHost(&sc->h_stage, want));
+        sc->h_stage_cap = want;
+    }
+    uint8_t *hs = sc->h_stage;
+    if (n) {
+        std::memcpy(hs + off_kind, d->body_kind, n);
+        std::memcpy(hs + off_geom, d->body_geom, (size_t)n * 64);
+    }
+    BodyMat *mats = reinterpret_cast<BodyMat *>(hs + off_mat);
+    double *sph = reinterpret_cast<double *>(hs + off_sph);
+    uint32_t *sph_body = reinterpret_cast<uint32_t *>(hs + off_sphb), *misc_body = reinterpret_cast<uint32_t *>(hs + off_misc);
+    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};   // bounding box of the finite sphere centres
+    bool have = false;
+    for (uint32_t i = 0, si = 0, mi = 0; i < n; ++i) {
         BodyMat &m = mats[i];
         std::memset(&m, 0, sizeof(m));
         for (int k = 0; k < 3; ++k) m.color[k] = d->color[3 * (size_t)i + k];
@@ -257,48 +353,21 @@ static int build_scene(rg_scene *sc, const rg_scene_desc *d) {
         m.surface = d->surface_kind[i];
         const double *g = d->body_geom + 8 * (size_t)i;
         if (d->body_kind[i] == RG_BODY_SPHERE) {
-            sph.insert(sph.end(), g, g + 4);
-            sph_body.push_back(i);
+            std::memcpy(sph + 4 * (size_t)si, g, 32);
+            sph_body[si++] = i;
+            if (std::isfinite(g[0]) && std::isfinite(g[1]) && std::isfinite(g[2])) {
+                for (int k = 0; k < 3; ++k) {
+                    if (!have) { lo[k] = hi[k] = g[k]; }
+                    else { lo[k] = std::fmin(lo[k], g[k]); hi[k] = std::fmax(hi[k], g[k]); }
+                }
+                have = true;
+            }
         } else {
-            misc_body.push_back(i);
+            misc_body[mi++] = i;
         }
     }
-    ds.n_spheres = (uint32_t)sph_body.size();
-    ds.n_misc = (uint32_t)misc_body.size();
-
-    // FP32 cull records (rg_cull.h).  P = centre of the bounding box of the sphere centres.
-    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
-    bool have = false;
-    for (uint32_t i = 0; i < ds.n_spheres; ++i) {
-        bool finite = true;
-        for (int k = 0; k < 3; ++k) finite = finite && std::isfinite(sph[4 * (size_t)i + k]);
-        if (!finite) continue;
-        for (int k = 0; k < 3; ++k) {
-            double c = sph[4 * (size_t)i + k];
-            if (!have) { lo[k] = hi[k] = c; }
-            else { lo[k] = std::fmin(lo[k], c); hi[k] = std::fmax(hi[k], c); }
-        }
-        have = true;
-    }
+    // P = centre of the bounding box of the sphere centres: reference point of the FP32 cull coordinates
     for (int k = 0; k < 3; ++k) ds.cull_ref[k] = have ? 0.5 * (lo[k] + hi[k]) : 0.0;
-    // padded to a multiple of kCullPad records that reject everything (K = +inf)
-    const size_t cull_padded = ((size_t)ds.n_spheres + 3) / 4 * 4;
-    std::vector<float4> cull(cull_padded, make_float4(0.f, 0.f, 0.f, std::numeric_limits<float>::infinity()));
-    for (uint32_t i = 0; i < ds.n_spheres; ++i) {
-        double cx = sph[4 * (size_t)i] - ds.cull_ref[0], cy = sph[4 * (size_t)i + 1] - ds.cull_ref[1],
-               cz = sph[4 * (size_t)i + 2] - ds.cull_ref[2], r = sph[4 * (size_t)i + 3];
-        double C2 = cx * cx + cy * cy + cz * cz, r2 = r * r;
-        float4 rec;
-        rec.x = (float)cx; rec.y = (float)cy; rec.z = (float)cz;
-        if (C2 < kCullHuge && r2 < kCullHuge) {   // also false for NaN
-            double K = (C2 - r2) - kCullU * (kCullSphereC2 * C2 + kCullSphereR2 * r2);
-            rec.w = (float)K;
-        } else {
-            rec.x = rec.y = rec.z = 0.0f;
-            rec.w = -std::numeric_limits<float>::infinity();   // never rejected
-        }
-        cull[i] = rec;
-    }
 
     for (uint32_t l = 0; l < d->n_lights; ++l) {
         DLight &L = ds.lights[l];
@@ -316,28 +385,34 @@ static int build_scene(rg_scene *sc, const rg_scene_desc *d) {
         L.intensity = d->light_intensity[l];
     }
 
-    int rc;
-    if ((rc = upload(sc, d->body_kind, n, &ds.kind))) return rc;
-    if ((rc = upload(sc, d->body_geom, 8 * (size_t)n, &ds.geom))) return rc;
-    if ((rc = upload(sc, mats.data(), mats.size(), &ds.mat))) return rc;
-    if ((rc = upload(sc, reinterpret_cast<const double4 *>(sph.data()), (size_t)ds.n_spheres, &ds.sph))) return rc;
-    if ((rc = upload(sc, sph_body.data(), sph_body.size(), &ds.sph_body))) return rc;
-    if ((rc = upload(sc, cull.data(), cull.size(), &ds.cull4))) return rc;
-    std::vector<float4> cull2(cull.size());   // pair-interleaved copy for the packed FFMA2 kernel
-    for (size_t k = 0; k + 1 < cull.size(); k += 2) {
-        cull2[k] = make_float4(cull[k].x, cull[k + 1].x, cull[k].y, cull[k + 1].y);
-        cull2[k + 1] = make_float4(cull[k].z, cull[k + 1].z, -cull[k].w, -cull[k + 1].w);
+    uint8_t *dev = static_cast<uint8_t *>(sc->arena.alloc(total));
+    float4 *cull4 = static_cast<float4 *>(sc->arena.alloc(std::max<size_t>(cull_padded, 1) * sizeof(float4)));
+    float4 *cull2 = static_cast<float4 *>(sc->arena.alloc(std::max<size_t>(cull_padded, 1) * sizeof(float4)));
+    if (!dev || !cull4 || !cull2) return RG_E_NOMEM;
+    RG_CUDA(cudaMemcpyAsync(dev, hs, total, cudaMemcpyHostToDevice, sc->stream));
+    ds.kind = n ? dev + off_kind : nullptr;
+    ds.geom = n ? reinterpret_cast<const double *>(dev + off_geom) : nullptr;
+    ds.mat = n ? reinterpret_cast<const BodyMat *>(dev + off_mat) : nullptr;
+    ds.sph = ns ? reinterpret_cast<const double4 *>(dev + off_sph) : nullptr;
+    ds.sph_body = ns ? reinterpret_cast<const uint32_t *>(dev + off_sphb) : nullptr;
+    ds.misc_body = nm ? reinterpret_cast<const uint32_t *>(dev + off_misc) : nullptr;
+    ds.cull4 = ns ? cull4 : nullptr;
+    ds.cull2 = ns ? cull2 : nullptr;
+    if (cull_padded) {
+        k_cull_records<<<(unsigned)((cull_padded + 255) / 256), 256, 0, sc->stream>>>(ds.sph, ns, (uint32_t)cull_padded, ds.cull_ref[0],
+                                                                                      ds.cull_ref[1], ds.cull_ref[2], cull4, cull2);
+        RG_CUDA(cudaGetLastError());
     }
-    if ((rc = upload(sc, cull2.data(), cull2.size(), &ds.cull2))) return rc;
-    if ((rc = upload(sc, misc_body.data(), misc_body.size(), &ds.misc_body))) return rc;
     static const bool dbg_timing = getenv("RG_DEBUG_TIMING") != nullptr;
     auto T0 = std::chrono::steady_clock::now();
+    int rc;
     if ((rc = create_textures(sc, d))) return rc;
     auto T1 = std::chrono::steady_clock::now();
-    if ((rc = grid_build(sc, sph, cull))) return rc;
+    if ((rc = grid_build(sc, sph, ns))) return rc;   // (synchronises the stream: the staging buffer is free again)
     if (dbg_timing)
         fprintf(stderr, "[build_scene] textures %.3f ms, grid %.3f ms\n", std::chrono::duration<double, std::milli>(T1 - T0).count(),
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T1).count());
+    RG_CUDA(cudaStreamSynchronize(sc->stream));
     return RG_OK;
 }
 
@@ -377,6 +452,17 @@ __global__ void __launch_bounds__(256) k_fma_peak(T *out, int iters, T a, T b, l
 using namespace rg;
 
 extern "C" {
+static int rg_render_rowlist_device_impl(rg_scene *sc, uint32_t w, uint32_t h, const uint32_t *rows, uint32_t n_rows, void *d_rgba_out,
+                                         void *cuda_stream, rg_stats *stats);
+}
+namespace rg {
+int rowlist_device_unguarded(rg_scene *sc, uint32_t w, uint32_t h, const uint32_t *rows, uint32_t n_rows, void *d_rgba_out,
+                             void *cuda_stream, rg_stats *stats) {
+    return rg_render_rowlist_device_impl(sc, w, h, rows, n_rows, d_rgba_out, cuda_stream, stats);
+}
+}  // namespace rg
+
+extern "C" {
 
 const char *rg_last_error(void) { return g_last_error.c_str(); }
 
@@ -395,7 +481,10 @@ void rg_scene_destroy(rg_scene *sc) {
     {
         std::lock_guard<std::mutex> lock(g_park_mutex);
         std::vector<ParkedContext> &parked = g_parked[sc->device];
-        if (parked.size() < kMaxParkedPerDevice && sc->stream) {   // park the device-side context for the next scene on this device
+        // park the device-side context for the next scene on this device — only a COMPLETE one (a create() that
+        // failed half-way must not hand its holes to the next scene)
+        const bool complete = sc->stream && sc->d_counters && sc->h_counters && sc->ev[0] && sc->ev[1] && sc->ev[2] && sc->ev[3];
+        if (parked.size() < kMaxParkedPerDevice && complete) {
             if (sc->h_frame) cudaFreeHost(sc->h_frame);
             parked.emplace_back();
             ParkedContext &slot = parked.back();
@@ -407,6 +496,8 @@ void rg_scene_destroy(rg_scene *sc) {
             slot.d_counters = sc->d_counters;
             slot.h_counters = sc->h_counters;
             slot.stream = sc->stream;
+            slot.h_stage = sc->h_stage;
+            slot.h_stage_cap = sc->h_stage_cap;
             for (int k = 0; k < 4; ++k) slot.ev[k] = sc->ev[k];
             delete sc;
             return;
@@ -417,6 +508,7 @@ void rg_scene_destroy(rg_scene *sc) {
     sc->frame.release();
     sc->rowlist.release();
     if (sc->h_frame) cudaFreeHost(sc->h_frame);
+    if (sc->h_stage) cudaFreeHost(sc->h_stage);
     if (sc->d_counters) cudaFree(sc->d_counters);
     if (sc->h_counters) cudaFreeHost(sc->h_counters);
     for (auto &e : sc->ev) if (e) cudaEventDestroy(e);
@@ -497,6 +589,8 @@ int rg_scene_create(const rg_scene_desc *desc, int32_t device, rg_scene **out) {
             sc->d_counters = slot.d_counters;
             sc->h_counters = slot.h_counters;
             sc->stream = slot.stream;
+            sc->h_stage = slot.h_stage;
+            sc->h_stage_cap = slot.h_stage_cap;
             for (int k = 0; k < 4; ++k) sc->ev[k] = slot.ev[k];
         }
     }
@@ -582,8 +676,9 @@ static int mega_render(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32
     RG_CUDA(cudaEventRecord(sc->ev[0], stream));
     if (npix) {
         const unsigned blocks = (unsigned)((npix + 127) / 128);
-        if (sc->ds.max_depth <= 12) k_render_mega<12><<<blocks, 128, 0, stream>>>(sc->ds, w, h, y0, y1, d_rows, d_out, sc->d_counters);
-        else k_render_mega<RG_MAX_DEPTH><<<blocks, 128, 0, stream>>>(sc->ds, w, h, y0, y1, d_rows, d_out, sc->d_counters);
+        float *f32 = sc->out_f32 ? reinterpret_cast<float *>(d_out) : nullptr;
+        if (sc->ds.max_depth <= 12) k_render_mega<12><<<blocks, 128, 0, stream>>>(sc->ds, w, h, y0, y1, d_rows, d_out, f32, sc->d_counters);
+        else k_render_mega<RG_MAX_DEPTH><<<blocks, 128, 0, stream>>>(sc->ds, w, h, y0, y1, d_rows, d_out, f32, sc->d_counters);
         RG_CUDA(cudaGetLastError());
     }
     RG_CUDA(cudaEventRecord(sc->ev[1], stream));
@@ -841,6 +936,105 @@ int rg_render(rg_scene *sc, uint32_t w, uint32_t h, uint8_t *rgba_out, rg_stats 
 int rg_render_stream(rg_scene *sc, uint32_t w, uint32_t h, uint32_t band_rows, rg_rows_cb cb, void *user, rg_stats *stats) {
     RG_ENTER(sc);
     return rg_render_stream_impl(sc, w, h, band_rows, cb, user, stats);
+}
+
+// ---- unquantised colours: RenderedPixel.color is an f32 Color (rendering.rs:18-22), quantised only by the consumer
+static int render_rows_f32_impl(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, float *rgb_out, rg_stats *stats) {
+    int rc = check_dims(sc, w, h, y0, y1);
+    if (rc) return rc;
+    if ((rc = single_device_only(sc, "rg_render_rows_f32"))) return rc;
+    if (!rgb_out && y1 > y0) { set_error("output pointer is NULL"); return RG_E_INVALID; }
+    RG_CUDA(cudaSetDevice(sc->device));
+    const size_t bytes = (size_t)(y1 - y0) * w * 12;
+    if ((rc = sc->frame.reserve(bytes ? bytes : 4))) return rc;
+    sc->out_f32 = true;
+    rc = render_device(sc, w, h, y0, y1, nullptr, sc->frame.ptr, sc->stream, stats);
+    sc->out_f32 = false;
+    if (rc) return rc;
+    if (bytes) {
+        RG_CUDA(cudaMemcpyAsync(rgb_out, sc->frame.ptr, bytes, cudaMemcpyDeviceToHost, sc->stream));
+        RG_CUDA(cudaStreamSynchronize(sc->stream));
+    }
+    return RG_OK;
+}
+
+int rg_render_rows_f32(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, float *rgb_out, rg_stats *stats) {
+    RG_ENTER(sc);
+    return render_rows_f32_impl(sc, w, h, y0, y1, rgb_out, stats);
+}
+
+int rg_render_stream_f32(rg_scene *sc, uint32_t w, uint32_t h, uint32_t band_rows, rg_rows_f32_cb cb, void *user, rg_stats *stats) {
+    RG_ENTER(sc);
+    int rc = check_dims(sc, w, h, 0, h);
+    if (rc) return rc;
+    if (!cb) { set_error("callback is NULL"); return RG_E_INVALID; }
+    if ((rc = single_device_only(sc, "rg_render_stream_f32"))) return rc;
+    RG_CUDA(cudaSetDevice(sc->device));
+    if (band_rows == 0) band_rows = (uint32_t)std::max<uint64_t>(1, (1ull << 20) / w);
+    if (band_rows > h) band_rows = h;
+    const size_t band_bytes = (size_t)band_rows * w * 12;
+    if (sc->h_frame_cap < band_bytes) {
+        if (sc->h_frame) cudaFreeHost(sc->h_frame);
+        sc->h_frame = nullptr;
+        sc->h_frame_cap = 0;
+        RG_CUDA(cudaMallocHost(&sc->h_frame, band_bytes));
+        sc->h_frame_cap = band_bytes;
+    }
+    rg_stats total;
+    std::memset(&total, 0, sizeof(total));
+    for (uint32_t y0 = 0; y0 < h; y0 += band_rows) {
+        const uint32_t y1 = y0 + band_rows < h ? y0 + band_rows : h;
+        rg_stats s;
+        std::memset(&s, 0, sizeof s);
+        rc = render_rows_f32_impl(sc, w, h, y0, y1, reinterpret_cast<float *>(sc->h_frame), &s);
+        if (rc) return rc;
+        accumulate(&total, s);
+        if (cb(y0, y1 - y0, w, reinterpret_cast<const float *>(sc->h_frame), user) != 0) {   // closed channel: rendering.rs:53-54,67
+            set_error("render cancelled by the row callback at row %u", y0);
+            if (stats) *stats = total;
+            return RG_E_CANCELLED;
+        }
+    }
+    if (stats) *stats = total;
+    return RG_OK;
+}
+
+int rg_render_rowlist_host(rg_scene *sc, uint32_t w, uint32_t h, const uint32_t *rows, uint32_t n_rows, uint8_t *frame, rg_stats *stats) {
+    RG_ENTER(sc);
+    int rc = check_dims(sc, w, h, 0, h);
+    if (rc) return rc;
+    if ((rc = single_device_only(sc, "rg_render_rowlist_host"))) return rc;
+    if (n_rows && (!rows || !frame)) { set_error("rows / frame pointer is NULL"); return RG_E_INVALID; }
+    RG_CUDA(cudaSetDevice(sc->device));
+    return render_rowlist_to_host(sc, w, h, rows, n_rows, frame, stats);
+}
+
+int rg_trim(void) { return (int)trim_parked(-1); }
+
+int rg_device_enable_peer(int32_t device, int32_t peer) {
+    int ndev = rg_device_count();
+    if (device < 0 || device >= ndev || peer < 0 || peer >= ndev) { set_error("device %d / peer %d out of range (%d devices)", device, peer, ndev); return RG_E_INVALID; }
+    if (device == peer) return RG_OK;
+    int can = 0;
+    RG_CUDA(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can) { set_error("GPU %d cannot address GPU %d's memory", device, peer); return RG_E_CUDA; }
+    RG_CUDA(cudaSetDevice(device));
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return RG_OK; }
+    RG_CUDA(e);
+    return RG_OK;
+}
+
+int rg_host_register(void *ptr, size_t bytes) {
+    if (!ptr || !bytes) { set_error("rg_host_register: bad argument"); return RG_E_INVALID; }
+    RG_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return RG_OK;
+}
+
+int rg_host_unregister(void *ptr) {
+    if (!ptr) return RG_OK;
+    RG_CUDA(cudaHostUnregister(ptr));
+    return RG_OK;
 }
 
 int rg_scene_create_multi(const rg_scene_desc *desc, const int32_t *devices, uint32_t n_devices, rg_scene **out) {

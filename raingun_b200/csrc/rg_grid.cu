@@ -5,6 +5,7 @@
 #include <cstring>
 #include <limits>
 
+#include "rg_cull.h"
 #include "rg_grid.cuh"
 #include "rg_host.h"
 
@@ -28,11 +29,23 @@ static int upload_vec(rg_scene *sc, const std::vector<T> &v, const T **out) {
     return RG_OK;
 }
 
-static int grid_build_host(rg_scene *sc, const std::vector<double> &sph, const std::vector<float4> &cull) {
+// the FP32 cull record of one sphere as k_cull_records (rg_api.cu) computes it on the device
+static float4 host_cull_record(const double *sp, const double *P) {
+    const double cx = sp[0] - P[0], cy = sp[1] - P[1], cz = sp[2] - P[2], r = sp[3];
+    const double C2 = cx * cx + cy * cy + cz * cz, r2 = r * r;
+    if (C2 < kCullHuge && r2 < kCullHuge) {
+        const double K = (C2 - r2) - kCullU * (kCullSphereC2 * C2 + kCullSphereR2 * r2);
+        return make_float4((float)cx, (float)cy, (float)cz, (float)K);
+    }
+    return make_float4(0.f, 0.f, 0.f, -std::numeric_limits<float>::infinity());
+}
+
+static int grid_build_host(rg_scene *sc, const double *sph, uint32_t n) {
     GridDev &g = sc->ds.grid;
     g = GridDev{};
-    const uint32_t n = sc->ds.n_spheres;
     if (n < 8) return RG_OK;   // brute force is the right tool for a handful of bodies
+    std::vector<float4> cull(n);
+    for (uint32_t i = 0; i < n; ++i) cull[i] = host_cull_record(sph + 4 * (size_t)i, sc->ds.cull_ref);
 
     // bounds of the finite spheres, relative to the cull reference point P
     const double *P = sc->ds.cull_ref;
@@ -315,10 +328,9 @@ __global__ void k_gb_sort_loose(const uint32_t *tmp, uint32_t n, uint32_t *out) 
     }
 }
 
-static int grid_build_device(rg_scene *sc, const std::vector<double> &sph) {
+static int grid_build_device(rg_scene *sc, const double *sph, uint32_t n) {
     GridDev &g = sc->ds.grid;
     g = GridDev{};
-    const uint32_t n = sc->ds.n_spheres;
     if (n < 8) return RG_OK;
     // host: bounding box of the binnable spheres and the resolution (same arithmetic as grid_build_host)
     const double *P = sc->ds.cull_ref;
@@ -402,9 +414,9 @@ static int grid_build_device(rg_scene *sc, const std::vector<double> &sph) {
     return RG_OK;
 }
 
-int grid_build(rg_scene *sc, const std::vector<double> &sph, const std::vector<float4> &cull) {
+int grid_build(rg_scene *sc, const double *sph, uint32_t n) {
     static const bool on_host = [] { const char *e = getenv("RG_GRID_BUILD"); return e && std::strcmp(e, "host") == 0; }();
-    return on_host ? grid_build_host(sc, sph, cull) : grid_build_device(sc, sph);
+    return on_host ? grid_build_host(sc, sph, n) : grid_build_device(sc, sph, n);
 }
 
 

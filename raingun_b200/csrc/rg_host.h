@@ -97,6 +97,8 @@ struct rg_scene {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     rg::DeviceBuffer frame;                // RGBA8 staging for host-buffer renders
     rg::DeviceBuffer rowlist;              // device copy of a caller's row list
+    uint8_t *h_stage = nullptr;            // pinned staging of the scene upload (one H2D copy per scene)
+    size_t h_stage_cap = 0;
     uint8_t *h_frame = nullptr;            // pinned staging
     size_t h_frame_cap = 0;
     rg::WavefrontScratch wf;
@@ -114,6 +116,7 @@ struct rg_scene {
     bool trace_stats = false;              // RG_OPT_TRACE_STATS
     uint32_t depth_hint = 0;               // levels the ray tree of this scene has been seen to use (0 = unknown)
     bool host_free_overflowed = false;     // a level once outgrew the default queue capacity: stay with the host-sized loop
+    bool out_f32 = false;                  // this call delivers unquantised f32 colours, 3 per pixel (rg_render_rows_f32)
     bool scatter_out = false;              // this call stores rows at their place in a full frame (rg_render_rowlist_scatter)
     // derived
     uint32_t n_bodies = 0;
@@ -125,12 +128,16 @@ namespace rg {
 // rows [y0, y1) of the image, or — when d_rows is given — entries [y0, y1) of that row list
 int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0, uint32_t y1,
                      const uint32_t *d_rows, uchar4 *d_out, cudaStream_t stream, rg_stats *st);
+// rg_api.cu: rg_render_rowlist_device without the one-render-at-a-time guard (for callers that hold it)
+int rowlist_device_unguarded(rg_scene *sc, uint32_t w, uint32_t h, const uint32_t *rows, uint32_t n_rows, void *d_rgba_out,
+                             void *cuda_stream, rg_stats *stats);
 // rg_multi.cu
+int render_rowlist_to_host(rg_scene *sc, uint32_t w, uint32_t h, const uint32_t *rows, uint32_t n_rows, uint8_t *frame, rg_stats *st);
 int multi_create(const rg_scene_desc *desc, const int32_t *devices, uint32_t n_devices, rg_scene **out);
 void multi_destroy(rg_scene *sc);
 int multi_set_option(rg_scene *sc, int32_t key, int64_t value);
 uint32_t multi_device_count(const rg_scene *sc);
 int multi_render_rows(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, uint8_t *rgba_out, rg_stats *stats);
 // rg_grid.cu
-int grid_build(rg_scene *sc, const std::vector<double> &sph /* n x 4 */, const std::vector<float4> &cull);
+int grid_build(rg_scene *sc, const double *sph /* n x 4, host */, uint32_t n);
 }  // namespace rg

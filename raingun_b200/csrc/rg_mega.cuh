@@ -40,7 +40,7 @@ __device__ __forceinline__ C3 mega_shade_diffuse(const DScene &s, uint32_t body,
 template <int STACK>
 __global__ void __launch_bounds__(128)
 k_render_mega(DScene s, uint32_t width, uint32_t height, uint32_t y0, uint32_t y1, const uint32_t *__restrict__ rows,
-              uchar4 *__restrict__ out, DCounters *ctr) {
+              uchar4 *__restrict__ out, float *__restrict__ out_f32, DCounters *ctr) {
     const uint64_t npix = (uint64_t)(y1 - y0) * width;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cnt[4] = {0, 0, 0, 0};   // primary, shadow, reflection, transmission
@@ -114,7 +114,8 @@ k_render_mega(DScene s, uint32_t width, uint32_t height, uint32_t y0, uint32_t y
                 }
             }
         }
-        out[i] = quantise(ret);
+        if (out_f32) { out_f32[3 * i] = ret.r; out_f32[3 * i + 1] = ret.g; out_f32[3 * i + 2] = ret.b; }   // RenderedPixel.color
+        else out[i] = quantise(ret);
     }
     // ray counters: warp-reduce, one atomic per warp per type
 #pragma unroll

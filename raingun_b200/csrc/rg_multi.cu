@@ -62,43 +62,63 @@ static void rows_of_tiles(const MultiJob &j, const std::vector<uint32_t> &tiles,
     }
 }
 
-// One batch on one device: render the rows compactly into the device's frame, then copy every run of
-// adjacent rows to its place in the caller's buffer.
+// Copies rows that lie compactly (in list order) in device memory to their own places in a host frame
+// (`frame` = address of image row 0): runs of adjacent rows travel as one copy each, and a list of
+// equal runs at a constant stride — an interleaved static share — as ONE strided copy.
+static int copy_rows_to_host(const uint8_t *d_src, const uint32_t *rows, size_t n_rows, uint8_t *frame, size_t row_bytes, cudaStream_t stream) {
+    struct Run { uint32_t row; uint32_t count; };
+    std::vector<Run> runs;
+    for (size_t k = 0; k < n_rows;) {
+        size_t e = k + 1;
+        while (e < n_rows && rows[e] == rows[e - 1] + 1) ++e;
+        runs.push_back({rows[k], (uint32_t)(e - k)});
+        k = e;
+    }
+    size_t r = 0, done_rows = 0;
+    if (runs.size() >= 3 && runs[1].row > runs[0].row) {
+        const uint32_t stride = runs[1].row - runs[0].row, cnt = runs[0].count;
+        size_t full = 1;
+        while (full < runs.size() && runs[full].count == cnt && runs[full].row - runs[full - 1].row == stride) ++full;
+        if (full >= 3) {
+            RG_CUDA(cudaMemcpy2DAsync(frame + (size_t)runs[0].row * row_bytes, (size_t)stride * row_bytes, d_src, (size_t)cnt * row_bytes,
+                                      (size_t)cnt * row_bytes, full, cudaMemcpyDeviceToHost, stream));
+            r = full;
+            done_rows = full * cnt;
+        }
+    }
+    for (; r < runs.size(); ++r) {
+        RG_CUDA(cudaMemcpyAsync(frame + (size_t)runs[r].row * row_bytes, d_src + done_rows * row_bytes, (size_t)runs[r].count * row_bytes,
+                                cudaMemcpyDeviceToHost, stream));
+        done_rows += runs[r].count;
+    }
+    return RG_OK;
+}
+
+// Renders the listed image rows on the scene's device and delivers each at its place in a HOST frame.
+int render_rowlist_to_host(rg_scene *sc, uint32_t w, uint32_t h, const uint32_t *rows, uint32_t n_rows, uint8_t *frame, rg_stats *st) {
+    if (n_rows == 0) { if (st) std::memset(st, 0, sizeof *st); return RG_OK; }
+    const size_t row_bytes = (size_t)w * 4;
+    int rc = sc->frame.reserve((size_t)n_rows * row_bytes);
+    if (rc) return rc;
+    rg_stats local;
+    std::memset(&local, 0, sizeof local);
+    rc = rowlist_device_unguarded(sc, w, h, rows, n_rows, sc->frame.ptr, sc->stream, &local);
+    if (rc) return rc;
+    if ((rc = copy_rows_to_host(static_cast<const uint8_t *>(sc->frame.ptr), rows, n_rows, frame, row_bytes, sc->stream))) return rc;
+    RG_CUDA(cudaStreamSynchronize(sc->stream));
+    if (st) *st = local;
+    return RG_OK;
+}
+
+// One batch on one device of a multi-GPU scene
 static int render_tiles_to_host(rg_scene *sc, const MultiJob &j, const std::vector<uint32_t> &tiles, std::vector<uint32_t> &rows,
                                 rg_stats *st) {
     rows_of_tiles(j, tiles, rows);
     if (rows.empty()) return RG_OK;
-    const size_t row_bytes = (size_t)j.w * 4;
-    int rc = sc->frame.reserve(rows.size() * row_bytes);
-    if (rc) return rc;
     rg_stats local;
-    std::memset(&local, 0, sizeof local);
-    rc = rg_render_rowlist_device(sc, j.w, j.h, rows.data(), (uint32_t)rows.size(), sc->frame.ptr, sc->stream, &local);
+    // j.out holds rows [y0, y1): address of image row 0 = out - y0 rows
+    const int rc = render_rowlist_to_host(sc, j.w, j.h, rows.data(), (uint32_t)rows.size(), j.out - (size_t)j.y0 * j.w * 4, &local);
     if (rc) return rc;
-    // equal-sized tiles at a constant stride (the static interleaved share): one strided copy
-    size_t k = 0;
-    const uint8_t *src = static_cast<const uint8_t *>(sc->frame.ptr);
-    if (tiles.size() >= 3) {
-        const uint32_t stride = tiles[1] - tiles[0];
-        size_t full = 0;
-        while (full < tiles.size() && (full == 0 || tiles[full] - tiles[full - 1] == stride) &&
-               j.y0 + (tiles[full] + 1) * j.tile_rows <= j.y1)
-            ++full;
-        if (full >= 3 && stride >= 1) {
-            const size_t tile_bytes = (size_t)j.tile_rows * row_bytes;
-            uint8_t *dst = j.out + (size_t)tiles[0] * tile_bytes;
-            RG_CUDA(cudaMemcpy2DAsync(dst, (size_t)stride * tile_bytes, src, tile_bytes, tile_bytes, full, cudaMemcpyDeviceToHost, sc->stream));
-            k = full * j.tile_rows;
-        }
-    }
-    while (k < rows.size()) {   // whatever is left: runs of adjacent rows
-        size_t e = k + 1;
-        while (e < rows.size() && rows[e] == rows[e - 1] + 1) ++e;
-        RG_CUDA(cudaMemcpyAsync(j.out + (size_t)(rows[k] - j.y0) * row_bytes, src + k * row_bytes, (e - k) * row_bytes,
-                                cudaMemcpyDeviceToHost, sc->stream));
-        k = e;
-    }
-    RG_CUDA(cudaStreamSynchronize(sc->stream));
     // accumulate
     st->rays_primary += local.rays_primary; st->rays_shadow += local.rays_shadow;
     st->rays_reflection += local.rays_reflection; st->rays_transmission += local.rays_transmission;

@@ -388,6 +388,18 @@ __global__ void __launch_bounds__(256) k_quantise(const float4 *__restrict__ nod
     }
 }
 
+// RenderedPixel.color (rendering.rs:18-22,59-65): the UNQUANTISED f32 colour of every pixel, 3 floats per pixel
+// row-major in the batch — what Scene::streaming_render sends down its channel.
+__global__ void __launch_bounds__(256) k_export_f32(const float4 *__restrict__ node_a, float *out, uint32_t npix, const PixelOrder po) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const uint32_t r = p / po.width, x = p - r * po.width;
+    const float4 a = node_a[po.index(x, r)];
+    out[3 * (size_t)p] = a.x;
+    out[3 * (size_t)p + 1] = a.y;
+    out[3 * (size_t)p + 2] = a.z;
+}
+
 // The same, fused with the gather of a sharded frame: batch row r belongs to image row
 // rows[row0 + r] and is stored at its place in a FULL frame that may live in another
 // GPU's memory (a CUDA-IPC mapping written over NVLink) or in pinned host memory: the "collective"
@@ -777,7 +789,9 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
         RG_CUDA(cudaGetLastError());
         st->gpu_launches++;
     }
-    if (sc->scatter_out)   // d_out is the base of the whole frame; this batch covers row-list entries [y0, y1)
+    if (sc->out_f32)
+        k_export_f32<<<blocks(npix), 256, 0, stream>>>(wf.nodes[0].as<float4>(), reinterpret_cast<float *>(d_out), npix, po);
+    else if (sc->scatter_out)   // d_out is the base of the whole frame; this batch covers row-list entries [y0, y1)
         k_quantise_scatter<<<blocks(((uint64_t)npix + 3) / 4), 256, 0, stream>>>(wf.nodes[0].as<float4>(), d_out, npix, d_rows, y0, po);
     else
         k_quantise<<<blocks(((uint64_t)npix + 3) / 4), 256, 0, stream>>>(wf.nodes[0].as<float4>(), d_out, npix, po);
@@ -1019,7 +1033,9 @@ static int enqueue_batch_dev(rg_scene *sc, const DevPlan &plan, uint32_t width, 
         RG_CUDA(cudaGetLastError());
         st->gpu_launches++;
     }
-    if (sc->scatter_out)
+    if (sc->out_f32)
+        k_export_f32<<<(npix + 255) / 256, 256, 0, stream>>>(wf.nodes[0].as<float4>(), reinterpret_cast<float *>(d_out), npix, po);
+    else if (sc->scatter_out)
         k_quantise_scatter<<<(unsigned)((((uint64_t)npix + 3) / 4 + 255) / 256), 256, 0, stream>>>(wf.nodes[0].as<float4>(), d_out, npix, d_rows, y0, po);
     else
         k_quantise<<<(unsigned)((((uint64_t)npix + 3) / 4 + 255) / 256), 256, 0, stream>>>(wf.nodes[0].as<float4>(), d_out, npix, po);
@@ -1034,7 +1050,7 @@ static std::vector<uint64_t> graph_key(const rg_scene *sc, const DevPlan &plan, 
                                        uint32_t npix, const uint32_t *d_rows, const uchar4 *d_out, bool use_grid) {
     const WavefrontScratch &wf = sc->wf;
     std::vector<uint64_t> k = {width, height, y0, npix, (uint64_t)(uintptr_t)d_rows, (uint64_t)(uintptr_t)d_out,
-                               (uint64_t)use_grid, (uint64_t)sc->scatter_out, (uint64_t)sc->ds.max_depth, (uint64_t)sc->overlap,
+                               (uint64_t)use_grid, (uint64_t)sc->scatter_out | ((uint64_t)sc->out_f32 << 1), (uint64_t)sc->ds.max_depth, (uint64_t)sc->overlap,
                                (uint64_t)sc->verify_cull, (uint64_t)sc->trace_stats, (uint64_t)plan.levels, (uint64_t)plan.bins.nbins};
     auto add = [&](const DeviceBuffer &b) { k.push_back((uint64_t)(uintptr_t)b.ptr); };
     add(wf.ray[0]); add(wf.ray[1]); add(wf.hit_t); add(wf.hit_body); add(wf.stage_ray); add(wf.stage_key); add(wf.stage_meta); add(wf.bins);
@@ -1135,7 +1151,9 @@ int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0,
             RG_CUDA(cudaStreamCreateWithFlags(&sc->wf.aux, cudaStreamNonBlocking));
         for (uint32_t y = y0; y < y1 && rc == RG_OK;) {
             const uint32_t ye = (uint32_t)std::min<uint64_t>((uint64_t)y + batch_rows, y1);
-            uchar4 *out = sc->scatter_out ? d_out : d_out + (size_t)(y - y0) * width;
+            // RGBA8: 4 bytes per pixel; f32 colours (rg_render_rows_f32): 12
+            uchar4 *out = sc->scatter_out ? d_out
+                        : reinterpret_cast<uchar4 *>(reinterpret_cast<unsigned char *>(d_out) + (size_t)(y - y0) * width * (sc->out_f32 ? 12 : 4));
             if (host_free) {
                 DevPlan plan;
                 const uint64_t npix64 = (uint64_t)(ye - y) * width;

@@ -151,6 +151,83 @@ class TileCounter:
         return self.chunks[idx] if idx < len(self.chunks) else None
 
 
+# Counter keys must never be reused: a key left over from an earlier frame is already past its last chunk, every
+# claim on it returns None and the stealable tiles would silently stay unrendered.  So a key is made of a
+# session nonce (rank 0 draws it once per store, the others read it) and a call sequence number that every rank
+# advances in step (render_frame_sharded is collective); `frame_id` is only a label.  Keys two calls old are
+# deleted by rank 0, and in the stealing schedule the rows all ranks rendered are added up and checked.
+_SESSIONS: dict = {}
+_CALL_SEQ = [0]
+
+
+def _session_nonce(store, rank: int) -> str:
+    sid = id(store)
+    if sid not in _SESSIONS:
+        if rank == 0:
+            import secrets
+            nonce = secrets.token_hex(8)
+            store.set("raingun/session", nonce)
+        else:
+            nonce = bytes(store.get("raingun/session")).decode()
+        _SESSIONS[sid] = nonce
+    return _SESSIONS[sid]
+
+
+class SharedHostFrame:
+    """One frame in HOST memory that every rank of the box writes its rows into: a shared-memory file mapped
+    and pinned (``rg_host_register``) in each process, so every GPU delivers its rows over its own PCIe link
+    (``Scene.render_rowlist_host``) and nothing is gathered on one GPU first.  Two frames alternate like
+    ``PeerFrames``.  Rank 0 reads the finished frame after the end-of-frame barrier."""
+
+    def __init__(self, width: int, height: int, rank: int, world: int, store=None, tag: str = "0", pin: bool = True) -> None:
+        import os
+
+        self.width, self.height, self.rank, self.world = width, height, rank, world
+        self.nbytes = width * height * 4
+        self.maps, self.paths, self.pinned = [], [], []
+        for k in range(2):
+            key = f"raingun/host_frame/{tag}/{k}"
+            if rank == 0:
+                path = f"/dev/shm/raingun_{os.getpid()}_{tag}_{k}"
+                with open(path, "wb") as f:
+                    f.truncate(self.nbytes)
+                if world > 1:
+                    (store or default_store()).set(key, path)
+            else:
+                path = bytes((store or default_store()).get(key)).decode()
+            mm = np.memmap(path, dtype=np.uint8, mode="r+", shape=(height, width, 4))
+            self.maps.append(mm)
+            self.paths.append(path)
+            if pin:
+                from . import host_register
+                host_register(mm.ctypes.data, self.nbytes)
+                self.pinned.append(mm.ctypes.data)
+
+    def ptr(self, frame_id: int) -> int:
+        return self.maps[frame_id & 1].ctypes.data
+
+    def array(self, frame_id: int) -> np.ndarray:
+        return self.maps[frame_id & 1]
+
+    def close(self) -> None:
+        import os
+
+        from . import host_unregister
+        if self.world > 1:
+            dist.barrier()
+        for p in self.pinned:
+            host_unregister(p)
+        self.pinned, self.maps = [], []
+        if self.world > 1:
+            dist.barrier()
+        if self.rank == 0:
+            for path in self.paths:
+                try:
+                    os.unlink(path)
+                except OSError:
+                    pass
+
+
 class PeerFrames:
     """Rank 0's frame buffers as every rank of the box sees them (CUDA IPC, written over NVLink).
     Two frames alternate (``frame_id & 1``): a rank that is already storing rows of frame k+1 cannot
@@ -213,6 +290,8 @@ class ShardResult:
     claims: int = 0
     schedule: str = ""                     # the schedule actually used ("auto" resolved)
     stats: list = field(default_factory=list)   # whatever render_rowlist returned, per call
+    rows_seen: int = 0                     # steal schedule: rows all ranks had reported when this rank finished
+    rows_total_key: str = ""
 
 
 def default_store():
@@ -240,6 +319,9 @@ def render_frame_sharded(render_rowlist: Union[Callable[[np.ndarray, torch.Tenso
     ``gather_mode``: ``"peer"`` — needs ``peer_frames``; the renderers are then called as
     ``render_rowlist(rows, frame_ptr)`` and must store row ``rows[k]`` at ``frame_ptr + rows[k]*width*4``
     (``Scene.render_rowlist_scatter``); the frame is complete on rank 0 after one barrier.
+    ``"host"`` — as ``"peer"`` with ``peer_frames`` a ``SharedHostFrame``: the renderers
+    (``Scene.render_rowlist_host``) copy every row to its place in ONE pinned host frame all ranks map, each GPU
+    over its own PCIe link; the frame is complete in rank 0's host memory after one barrier.
     ``"reduce"`` — every rank scatters its rows into a zeroed full frame and ONE
     NCCL reduce (MAX over disjoint rows, i.e. a gather that needs no ownership exchange) lands the
     frame on rank 0 over NVLink; ``"p2p"`` — the row lists travel through the store and rank 0
@@ -251,9 +333,10 @@ def render_frame_sharded(render_rowlist: Union[Callable[[np.ndarray, torch.Tenso
     row_bytes = width * 4
     renderers = list(render_rowlist) if isinstance(render_rowlist, (list, tuple)) else [render_rowlist]
     workers = len(renderers)
-    peer = gather_mode == "peer"
+    host = gather_mode == "host"     # like "peer", but the shared frame lives in pinned host memory (SharedHostFrame)
+    peer = gather_mode == "peer" or host
     if peer and peer_frames is None:
-        raise ValueError("gather_mode='peer' needs peer_frames")
+        raise ValueError(f"gather_mode={gather_mode!r} needs peer_frames")
     if staging is None and not peer:
         staging = torch.empty((height * row_bytes,), dtype=torch.uint8, device=device)
     # first[k]: the batch worker k starts with (no counter traffic); claim(): the stealable rest
@@ -264,7 +347,11 @@ def render_frame_sharded(render_rowlist: Union[Callable[[np.ndarray, torch.Tenso
         if store is None:
             store = default_store()
         per_rank, tail_chunks = hybrid_plan(nt, world, min_chunk=2 if workers == 1 else 1)
-        counter = TileCounter(store, f"raingun/tiles/{frame_id}", tail_chunks)
+        _CALL_SEQ[0] += 1
+        seq = _CALL_SEQ[0]
+        prefix = f"raingun/{_session_nonce(store, rank)}"
+        steal_key = f"{prefix}/tiles/{seq}"
+        counter = TileCounter(store, steal_key, tail_chunks)
         first = split_share(per_rank[rank], workers, lead)
         claim = counter.claim
     elif schedule == "static":
@@ -306,12 +393,35 @@ def render_frame_sharded(render_rowlist: Union[Callable[[np.ndarray, torch.Tenso
     filled_rows = state["filled"]
     my_rows = [r for _, r in sorted(my_rows, key=lambda ar: ar[0])]   # staging order
     rows_all = np.concatenate(my_rows) if my_rows else np.zeros(0, np.uint32)
+    if world > 1 and schedule == "steal":
+        # every row must have been rendered by exactly one rank: add up what the ranks did (the barrier of the
+        # gather below — or the caller's — orders the read after every rank's add), drop counters two calls old
+        total = int(store.add(f"{prefix}/rows/{seq}", int(rows_all.size)))
+        res.rows_total_key = f"{prefix}/rows/{seq}"
+        if rank == 0 and seq > 2:
+            for old_key in (f"{prefix}/tiles/{seq - 2}", f"{prefix}/rows/{seq - 2}"):
+                try:
+                    store.delete_key(old_key)
+                except Exception:   # not every store can delete
+                    pass
+        res.rows_seen = total   # a lower bound until every rank has added; checked after the barrier
     if not gather:
         return res
-    if peer:   # the rows are already in rank 0's frame; make that known
+    def check_all_rows_rendered():
+        if world > 1 and schedule == "steal":
+            total = int(store.add(res.rows_total_key, 0))
+            if total != height:
+                raise RuntimeError(f"sharded frame {frame_id}: the ranks rendered {total} rows of {height} "
+                                   "(work-stealing counter out of step)")
+
+    if peer:   # the rows are already in rank 0's frame (GPU memory, or pinned host memory); make that known
         if world > 1:
             dist.barrier()
-        res.frame = peer_frames.tensor(frame_id) if rank == 0 else None
+        check_all_rows_rendered()
+        if host:
+            res.frame = torch.from_numpy(peer_frames.array(frame_id)) if rank == 0 else None
+        else:
+            res.frame = peer_frames.tensor(frame_id) if rank == 0 else None
         return res
 
     # ---- gather: ownership is dynamic, so the row lists travel first (tiny), then the pixels
@@ -326,6 +436,8 @@ def render_frame_sharded(render_rowlist: Union[Callable[[np.ndarray, torch.Tenso
         _scatter_rows(frame, rows_all, packed, width)
         dist.reduce(frame, dst=0, op=dist.ReduceOp.MAX)
         res.frame = frame if rank == 0 else None
+        if rank == 0:
+            check_all_rows_rendered()
         return res
     if store is None:
         store = default_store()
@@ -345,6 +457,7 @@ def render_frame_sharded(render_rowlist: Union[Callable[[np.ndarray, torch.Tenso
         for r, buf in recv_bufs.items():
             _scatter_rows(frame, lists[r], buf, width)
         res.frame = frame
+        check_all_rows_rendered()
     elif filled_rows:
         for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, packed, 0)]):
             req.wait()

@@ -102,8 +102,8 @@ def test_headers_are_plain_c(tmp_path):
         "    /* take the address of every entry point a host would bind */\n"
         "    void *fns[] = {(void *)rg_scene_create, (void *)rg_scene_create_multi, (void *)rg_scene_device_count, (void *)rg_scene_destroy, (void *)rg_scene_set_option, (void *)rg_render,\n"
         "                   (void *)rg_render_rows, (void *)rg_render_rows_device, (void *)rg_render_rowlist_device,\n"
-        "                   (void *)rg_render_rowlist_scatter, (void *)rg_shared_frame_create, (void *)rg_shared_frame_open,\n"
-        "                   (void *)rg_shared_frame_close, (void *)rg_render_stream, (void *)rg_last_error, (void *)rg_device_count,\n"
+        "                   (void *)rg_render_rowlist_scatter, (void *)rg_render_rowlist_host, (void *)rg_host_register, (void *)rg_host_unregister, (void *)rg_device_enable_peer, (void *)rg_shared_frame_create, (void *)rg_shared_frame_open,\n"
+        "                   (void *)rg_shared_frame_close, (void *)rg_render_stream, (void *)rg_render_rows_f32, (void *)rg_render_stream_f32, (void *)rg_trim, (void *)rg_last_error, (void *)rg_device_count,\n"
         "                   (void *)rgh_scene_load, (void *)rgh_scene_parse, (void *)rgh_scene_desc, (void *)rgh_scene_destroy,\n"
         "                   (void *)rgh_jpeg_decode, (void *)rgh_png_decode, (void *)rgh_png_encode, (void *)rgh_image_open,\n"
         "                   (void *)rgh_png_save, (void *)rgh_cli_parse, (void *)rgh_last_error, (void *)rgh_free};\n"
@@ -136,8 +136,8 @@ def test_rust_sys_crate_mirrors_the_header():
 
     for name in ("rg_texture_desc", "rg_scene_desc", "rg_stats"):
         assert c_fields(name) == rs_fields(name), name
-    c_fns = set(re.findall(r"\b(rg_[a-z_]+)\s*\(", hdr)) - {"rg_rows_cb"}
-    rs_fns = set(re.findall(r"pub fn (rg_[a-z_]+)\(", rs))
+    c_fns = set(re.findall(r"\b(rg_[a-z_0-9]+)\s*\(", hdr)) - {"rg_rows_cb", "rg_rows_f32_cb"}
+    rs_fns = set(re.findall(r"pub fn (rg_[a-z_0-9]+)\(", rs))
     assert c_fns == rs_fns == set(_native.EXPORTS)
 
 

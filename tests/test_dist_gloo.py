@@ -38,21 +38,44 @@ def _worker(rank, world, port, schedule, out_dir, gather_mode="p2p", workers=1):
         calls.append(len(rows))
         return len(rows)
 
+    host_frames = None
+    if gather_mode == "host":   # one shared host frame every rank writes its rows into (pinning needs CUDA: off here)
+        import ctypes
+
+        from raingun_b200.dist import SharedHostFrame
+        host_frames = SharedHostFrame(W, H, rank, world, pin=False)
+
+        def render_rowlist(rows, frame_ptr):   # noqa: F811 - the "host" flavour: row y goes to frame_ptr + y * W * 4
+            frame = np.ctypeslib.as_array(ctypes.cast(frame_ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(H, W, 4))
+            for y in rows:
+                frame[int(y)] = O.render_rows(data, W, H, int(y), int(y) + 1, threads=1)[0][0]
+            calls.append(len(rows))
+            return len(rows)
+
     tiles = []
-    for frame_id in (1, 2):   # two frames: the counter keys must not collide
+    # frame ids repeat on purpose: a restarted render loop reuses them, and the work-stealing counter keys
+    # must not (a reused key is already past its last chunk: the stealable tiles would silently stay unrendered)
+    for it, frame_id in enumerate((1, 2, 1, 1)):
         res = render_frame_sharded(render_rowlist if workers == 1 else [render_rowlist] * workers, W, H, rank, world,
                                    frame_id, torch.device("cpu"),
-                                   tile_rows=TILE, schedule=schedule, gather_mode=gather_mode)
+                                   tile_rows=TILE, schedule=schedule, gather_mode=gather_mode, peer_frames=host_frames)
         tiles.append(sorted(res.my_tiles))
         if rank == 0:
-            np.save(os.path.join(out_dir, f"frame{frame_id}.npy"), res.frame.numpy())
+            np.save(os.path.join(out_dir, f"frame{it}.npy"), np.array(res.frame.numpy()))
+        if host_frames is not None:
+            dist.barrier()           # rank 0 has copied the frame out before anyone overwrites it
+            host_frames.array(frame_id)[:] = 0
+            dist.barrier()
+    if host_frames is not None:
+        host_frames.close()
     np.save(os.path.join(out_dir, f"tiles{rank}.npy"), np.array(tiles[0], dtype=np.int64))
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("schedule,gather_mode,workers", [("steal", "p2p", 1), ("static", "p2p", 1), ("steal", "reduce", 1),
-                                                          ("steal", "reduce", 2), ("static", "p2p", 3)])
+                                                          ("steal", "reduce", 2), ("static", "p2p", 3), ("steal", "host", 1),
+                                                          ("static", "host", 2)])
 def test_two_ranks_reassemble_the_frame(tmp_path, oracle, schedule, gather_mode, workers):
     """workers > 1: several batches in flight per rank (one host thread each) claim from the same counter."""
     world = 2
@@ -61,8 +84,8 @@ def test_two_ranks_reassemble_the_frame(tmp_path, oracle, schedule, gather_mode,
 
     data, _ = make_scene("C4", spheres=40, depth=4)
     ref, _, _ = oracle.render(data, W, H)
-    for frame_id in (1, 2):
-        assert np.array_equal(np.load(tmp_path / f"frame{frame_id}.npy"), ref)
+    for it in range(4):
+        assert np.array_equal(np.load(tmp_path / f"frame{it}.npy"), ref), f"frame {it}"
     t0, t1 = np.load(tmp_path / "tiles0.npy"), np.load(tmp_path / "tiles1.npy")
     assert sorted(t0.tolist() + t1.tolist()) == list(range(n_tiles(H, TILE)))   # every tile exactly once
     if schedule == "static":

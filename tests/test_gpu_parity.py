@@ -245,6 +245,31 @@ def test_streaming_render_bands_and_cancel():
         assert calls == [0]     # cancelled after the first band (closed channel, rendering.rs:53-54,67)
 
 
+def test_unquantised_f32_colours_match_oracle_bit_for_bit(oracle):
+    """RenderedPixel.color is an f32 Color (rendering.rs:18-22,59-65): rg_render_rows_f32 / rg_render_stream_f32 deliver
+    the colour before Color::rgba narrows it.  Every float must carry the oracle's bits, in every pipeline."""
+    for name, data, w, h in (("test1", example_scene("test1"), 200, 150),
+                             ("C4-small", make_scene("C4", spheres=300, depth=6)[0], 192, 108)):
+        _, _, ref = oracle.render(data, w, h, want_f32=True)
+        for label, pipeline, accel in MODES:
+            with rg.Scene(data) as sc:
+                sc.set_pipeline(pipeline)
+                sc.set_accel(accel)
+                got = sc.render_rows_f32(w, h)
+                assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), f"{name}/{label}"
+                band = sc.render_rows_f32(w, h, 11, 60)
+                assert np.array_equal(band.view(np.uint32), ref[11:60].view(np.uint32)), f"{name}/{label} band"
+                acc = np.zeros_like(ref)
+                assert sc.streaming_render_f32(w, h, lambda y0, rows: acc.__setitem__(slice(y0, y0 + rows.shape[0]), rows) or True,
+                                               band_rows=37) is True
+                assert np.array_equal(acc.view(np.uint32), ref.view(np.uint32)), f"{name}/{label} stream"
+                calls = []
+                assert sc.streaming_render_f32(w, h, lambda y0, rows: calls.append(y0) or False, band_rows=50) is False
+                assert calls == [0]
+                rgba = sc.render_image(w, h)   # the quantised entry point still works on the same handle
+                assert (rgba[..., 3] == 255).all()
+
+
 def test_scatter_rows_odd_width(oracle):
     """rg_render_rowlist_scatter with a width that is not a multiple of 4 (scalar store path) and rows in
     arbitrary order, into a SharedFrame (the buffer other ranks would map through CUDA IPC)."""
@@ -420,6 +445,59 @@ def test_full_size_c5_row_matches_oracle(oracle):
     y = 2600
     ref, _, _ = oracle.render_rows(data, spec.width, spec.height, y, y + 1)
     assert np.array_equal(img[y:y + 1], ref)
+
+
+def test_c5_all_100k_spheres_grid_equals_verbatim_scan():
+    """configs[4] with ALL 100,000 spheres (a grid near its 256-cells-per-axis cap, chained cell records, textured
+    spheres, 4 spherical lights) on a whole 480x270 frame: the grid tracer's image and ray counts equal the
+    megakernel's (the reference recursion with every body tested in FP64, itself oracle-checked above), and
+    RG_OPT_VERIFY_CULL=2 — every traced ray re-traced on the device with the verbatim scan — finds no difference."""
+    data, _ = make_scene("C5", texture_loader=bundled_texture_loader)
+    w, h = 480, 270
+    mega, mst = _render(data, w, h, rg.PIPELINE_MEGAKERNEL, rg.ACCEL_BRUTE)
+    grid, gst = _render(data, w, h, rg.PIPELINE_WAVEFRONT, rg.ACCEL_GRID)
+    assert np.array_equal(grid, mega)
+    assert (gst.rays_primary, gst.rays_shadow, gst.rays_reflection, gst.rays_transmission) == (
+        mst.rays_primary, mst.rays_shadow, mst.rays_reflection, mst.rays_transmission)
+    with rg.Scene(data) as sc:
+        sc.set_pipeline(rg.PIPELINE_WAVEFRONT)
+        sc.set_accel(rg.ACCEL_GRID)
+        sc.set_option(rg._native.OPT_VERIFY_CULL, 2)
+        img = sc.render_image(w, h)
+        assert sc.last_stats.cull_unsound == 0
+    assert np.array_equal(img, mega)
+
+
+def test_peer_store_gather_across_two_devices():
+    """The fused gather on real hardware: a scene on GPU 1 stores its rows straight into a frame that lives on
+    GPU 0 (rg_render_rowlist_scatter over NVLink peer access), GPU 0 renders the rest; the assembled frame must
+    equal the one-GPU frame byte for byte.  Needs two GPUs (skipped on a one-GPU box)."""
+    import torch
+
+    if rg.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    if not torch.cuda.can_device_access_peer(1, 0):
+        pytest.skip("no peer access between GPU 1 and GPU 0")
+    data, _ = make_scene("C4", spheres=2000, depth=8)
+    w, h = 1280, 720
+    with rg.Scene(data, device=0) as sc:
+        sc.set_pipeline(rg.PIPELINE_WAVEFRONT)
+        ref = sc.render_image(w, h)
+    frame = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda:0")
+    rg._native.check(rg._native.lib().rg_device_enable_peer(1, 0))   # kernels on GPU 1 may store into GPU 0's memory
+    tiles = [np.arange(y, min(h, y + 8), dtype=np.uint32) for y in range(0, h, 8)]
+    rows0 = np.concatenate(tiles[0::2])
+    rows1 = np.concatenate(tiles[1::2])
+    with rg.Scene(data, device=0) as s0, rg.Scene(data, device=1) as s1:
+        for s_ in (s0, s1):
+            s_.set_pipeline(rg.PIPELINE_WAVEFRONT)
+        with torch.cuda.device(1):
+            s1.render_rowlist_scatter(w, h, rows1, frame.data_ptr(), torch.cuda.current_stream(1).cuda_stream)
+        with torch.cuda.device(0):
+            s0.render_rowlist_scatter(w, h, rows0, frame.data_ptr(), torch.cuda.current_stream(0).cuda_stream)
+    torch.cuda.synchronize(1)
+    torch.cuda.synchronize(0)
+    assert np.array_equal(frame.cpu().numpy(), ref)
 
 
 def test_degenerate_scenes(oracle):
