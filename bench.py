@@ -385,6 +385,28 @@ def main() -> int:
             dist.barrier()
             torch.cuda.synchronize(device)
 
+    section = [0]
+
+    def rank0_only(work):
+        """Runs `work()` on rank 0 while the other ranks wait ON THE CPU (a key in the c10d store): an NCCL barrier
+        would park a spinning kernel on every idle GPU, and the rank-0 sections below use those GPUs themselves."""
+        barrier()
+        section[0] += 1
+        result = None
+        if world == 1:
+            return work()
+        store = dist.distributed_c10d._get_default_store()
+        key = f"raingun/bench/section{section[0]}"
+        if rank == 0:
+            try:
+                result = work()
+            finally:
+                store.set(key, b"done")
+        else:
+            store.wait([key])
+        barrier()
+        return result
+
     def reduce_max(x: float) -> float:
         if world == 1:
             return x
@@ -580,9 +602,11 @@ def main() -> int:
     # ---- the same frame rendered on all N GPUs INSIDE the library (rank 0 only; the other ranks idle at the
     # barrier): rg_scene_create_multi + rg_render — what a host without torchrun gets (rendering.rs:27-35)
     in_library = None
-    if world > 1 and not args.no_in_library:
-        barrier()
-        if rank == 0 and rg.device_count() >= world:
+
+    def in_library_arm():
+        if rg.device_count() < world:
+            return None
+        if True:
             in_library = {}
             for label, schedule in (("static", 1), ("steal", 2)):
                 with rg.Scene(data, devices=list(range(world))) as msc:
@@ -602,7 +626,10 @@ def main() -> int:
             in_library["what"] = ("one process, one library thread per GPU, row tiles owned statically (static) or a 1/16 tail claimed "
                                   "from a std::atomic counter (steal); scene already uploaded; timed: rg_render into pinned host memory, "
                                   "every GPU copying its rows over its own PCIe link (wall clock)")
-        barrier()
+        return in_library
+
+    if world > 1 and not args.no_in_library:
+        in_library = rank0_only(in_library_arm)
 
     # ---- roofline arm (rank 0): the reference algorithm itself — brute force, every ray x every
     # body — whose dominant kernel k_trace_brute is FP32-pipe bound.
@@ -653,10 +680,7 @@ def main() -> int:
     # ---- every BASELINE.json config in the one run (rank 0; the other ranks idle at the barrier) ----------
     configs = None
     if not args.no_configs:
-        barrier()
-        if rank == 0:
-            configs = run_configs(rg, _native, torch, device, local_rank, world, sha)
-        barrier()
+        configs = rank0_only(lambda: run_configs(rg, _native, torch, device, local_rank, world, sha))
 
     # ---- the kernel behind `value` (k_trace_grid) against ITS ceiling: lane-issue slots -------------------
     grid_roofline = None

@@ -309,6 +309,14 @@ static int build_scene(rg_scene *sc, const rg_scene_desc *d) {
     ds.fov_adj = fov_adjustment(d->fov);
     for (int k = 0; k < 3; ++k) ds.default_color[k] = d->default_color[k];
 
+    static const bool dbg_timing = getenv("RG_DEBUG_TIMING") != nullptr;
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!dbg_timing) return;
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[build_scene] %-14s %.3f ms\n", what, std::chrono::duration<double, std::milli>(t - T0).count());
+        T0 = t;
+    };
     uint32_t ns = 0;
     for (uint32_t i = 0; i < n; ++i) ns += d->body_kind[i] == RG_BODY_SPHERE ? 1u : 0u;
     const uint32_t nm = n - ns;
@@ -385,6 +393,7 @@ static int build_scene(rg_scene *sc, const rg_scene_desc *d) {
         L.intensity = d->light_intensity[l];
     }
 
+    lap("host flatten");
     uint8_t *dev = static_cast<uint8_t *>(sc->arena.alloc(total));
     float4 *cull4 = static_cast<float4 *>(sc->arena.alloc(std::max<size_t>(cull_padded, 1) * sizeof(float4)));
     float4 *cull2 = static_cast<float4 *>(sc->arena.alloc(std::max<size_t>(cull_padded, 1) * sizeof(float4)));
@@ -403,15 +412,13 @@ static int build_scene(rg_scene *sc, const rg_scene_desc *d) {
                                                                                       ds.cull_ref[1], ds.cull_ref[2], cull4, cull2);
         RG_CUDA(cudaGetLastError());
     }
-    static const bool dbg_timing = getenv("RG_DEBUG_TIMING") != nullptr;
-    auto T0 = std::chrono::steady_clock::now();
+    lap("enqueue upload");
+    if (dbg_timing) { cudaStreamSynchronize(sc->stream); lap("(upload done)"); }
     int rc;
     if ((rc = create_textures(sc, d))) return rc;
-    auto T1 = std::chrono::steady_clock::now();
+    lap("textures");
     if ((rc = grid_build(sc, sph, ns))) return rc;   // (synchronises the stream: the staging buffer is free again)
-    if (dbg_timing)
-        fprintf(stderr, "[build_scene] textures %.3f ms, grid %.3f ms\n", std::chrono::duration<double, std::milli>(T1 - T0).count(),
-                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T1).count());
+    lap("grid");
     RG_CUDA(cudaStreamSynchronize(sc->stream));
     return RG_OK;
 }
@@ -721,6 +728,7 @@ static int render_device(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint
     if (mega) rc = mega_render(sc, w, h, y0, y1, d_rows, (uchar4 *)d_rgba_out, stream, &local);
     else rc = wavefront_render(sc, w, h, y0, y1, d_rows, (uchar4 *)d_rgba_out, stream, &local);
     local.pipeline_used = mega ? RG_PIPELINE_MEGAKERNEL : RG_PIPELINE_WAVEFRONT;
+    local.devices_used = 1;
     local.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (stats) *stats = local;
     return rc;

@@ -7,27 +7,33 @@
 // conservative cull and then the reference's exact FP64 test.  The result is the same
 // lexicographic (distance, body index) minimum as the brute-force scan.
 //
-// Why no hit can be missed (DESIGN.md "grid"):
-//   * a sphere is listed in every cell its bounding box, inflated by kGridInflate cells,
-//     overlaps; FP32 traversal error is bounded by ~3e-4 cell (|grid coords| <= kGridMaxCoord),
-//     far below the inflation, so the cell containing a hit point — or a neighbour the
-//     inflated box also covers — is always visited;
-//   * the walk stops only when the best exact distance lies before the current cell's exit
-//     (with slack), so every sphere that could be nearer has been listed in a visited cell;
+// Why no hit can be missed (derivation: DESIGN.md section 4.2):
+//   * a sphere is listed in every cell its bounding box, inflated by 2 * kGridInflate = 4e-3 cell,
+//     overlaps (binning is done in FP64);
+//   * the FP32 walk follows the true ray to within 8.1e-4 cell in every axis (u = 2^-24, grid
+//     coordinates <= 1024 in magnitude, <= 256 cells per axis: origin and direction rounding
+//     u * 8197, boundary parameters u * 5380), so every point of the true ray lies within that distance
+//     of a cell the walk visits, and a sphere hit there is listed in that cell;
+//   * the walk stops only at the entry of a cell whose entry parameter lies beyond the best exact
+//     distance (with slack): everything nearer lies in — or within the same 8.1e-4 cell of — a cell
+//     visited before;
 //   * rays the argument does not cover (direction not unit within 1e-9 — reflections off
-//     un-normalised plane normals — non-finite or far-away origins) skip the grid and scan
-//     every sphere exactly;
+//     un-normalised plane normals — non-finite origins, origins farther than 1e9 cells) skip the
+//     grid and scan every sphere exactly; origins farther than 1024 cells are first moved along
+//     the ray, in FP64, to one cell before the grid box;
 //   * spheres too large for the grid ("loose") and all non-sphere bodies are tested per ray.
 //
 // Execution model.  Ray lengths differ wildly (a lit shadow ray crosses the whole grid, an
 // occluded one stops after a few cells) and the exact FP64 test is ~10x a cull test, so a
 // one-thread-per-ray loop leaves most lanes of a warp idle (measured: 6 of 32 active).  The
-// kernel therefore runs PERSISTENT warps:
-//   * lanes whose ray is finished fetch new rays from a global counter (warp ballot + one
-//     atomic per refill) instead of waiting for the slowest lane;
-//   * a lane that finds a cull survivor parks it ("pending") and keeps nothing else going;
-//     the warp evaluates pending candidates together, so the expensive exact test runs with
-//     many lanes active instead of one.
+// kernel therefore runs PERSISTENT warps, and every phase is written so that the lanes that take
+// part run ONE instruction stream (a path that is rare per lane is frequent per warp: the SIMT tax):
+//   * lanes whose ray is finished retire it and fetch new rays from a global counter (warp ballot +
+//     one atomic per refill) instead of waiting for the slowest lane;
+//   * scanning lanes fetch one 48-byte record per step — a new cell's first record or the next
+//     chained record of a crowded cell, the same code either way — and cull its two items;
+//   * a lane that finds a cull survivor parks it ("pending"); the warp evaluates pending
+//     candidates together, so the expensive exact test runs with many lanes active instead of one.
 #pragma once
 #include "rg_trace.cuh"
 
@@ -174,7 +180,8 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
                     const double gz = (op.z - (double)g.lo[2]) * (double)g.inv_cell[2];
                     const double lim = 0.5 * (double)kGridMaxCoord;
                     const bool near_box = fabs(gx) <= lim && fabs(gy) <= lim && fabs(gz) <= lim;   // false on NaN
-                    const bool finite = fabs(gx) < 1e30 && fabs(gy) < 1e30 && fabs(gz) < 1e30;
+                    // (beyond 1e9 cells the FP64 move along the ray would itself cost more than 1e-6 cell: such rays scan every sphere)
+                    const bool finite = fabs(gx) < 1e9 && fabs(gy) < 1e9 && fabs(gz) < 1e9;
                     if (!near_box && finite) {
                         const double ddx = ray.d.x * (double)g.inv_cell[0], ddy = ray.d.y * (double)g.inv_cell[1],
                                      ddz = ray.d.z * (double)g.inv_cell[2];

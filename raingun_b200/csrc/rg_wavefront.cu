@@ -1073,6 +1073,7 @@ static int graph_batch(rg_scene *sc, const DevPlan &plan, uint32_t width, uint32
     if (!hit) {
         bool seen = false;
         for (auto &k : gc.seen) seen = seen || k == key;
+        if (getenv("RG_DEBUG_GRAPH")) fprintf(stderr, "[graph] dev %d key npix %u y0 %u rows %p out %p levels %u: %s\n", sc->device, npix, y0, (const void *)d_rows, (void *)d_out, plan.levels, seen ? "capture" : "first sight");
         if (!seen) {   // first time: run it eagerly (also warms every lazily initialised launch path)
             if (gc.seen.size() >= 32) gc.seen.erase(gc.seen.begin());
             gc.seen.push_back(key);
@@ -1088,6 +1089,7 @@ static int graph_batch(rg_scene *sc, const DevPlan &plan, uint32_t width, uint32
         const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
         sync_events.used = sync_used;
         if (rc != RG_OK || ce != cudaSuccess || !graph) {
+            if (getenv("RG_DEBUG_GRAPH")) fprintf(stderr, "[graph] capture failed: rc %d, cuda %d (%s)\n", rc, (int)ce, cudaGetErrorString(ce));
             if (graph) cudaGraphDestroy(graph);
             cudaGetLastError();
             sc->graph = 1;   // capture is not possible here: stay with eager launches
