@@ -142,9 +142,6 @@ enum {
     RG_OPT_GRAPH = 8,        /* replay the host-free frame as one CUDA graph: 0 = automatic, 1 = off, 2 = on */
     RG_OPT_TRACE_STATS = 9,  /* 1 = the grid tracer counts cells / fetches / cull tests / lane use
                                 (rg_stats.grid_*); an instrumented kernel, slower; results unchanged */
-    RG_OPT_REORDER = 10,     /* bin every level's children by origin region and direction octant before they
-                                are traced (host-free loop, grid tracer): 0 = automatic (off: it does not pay),
-                                1 = off, 2 = on */
     RG_OPT_SCHEDULE = 11,    /* multi-GPU scenes: 0 = automatic, 1 = static (tile t on device t mod N),
                                 2 = static share + a stealable tail handed out by an atomic tile counter */
     RG_OPT_TILE_ROWS = 12    /* multi-GPU scenes: rows per tile (default 8) */

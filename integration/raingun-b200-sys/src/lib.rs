@@ -42,7 +42,6 @@ pub const RG_OPT_OVERLAP: i32 = 6;
 pub const RG_OPT_HOST_FREE: i32 = 7;
 pub const RG_OPT_GRAPH: i32 = 8;
 pub const RG_OPT_TRACE_STATS: i32 = 9;
-pub const RG_OPT_REORDER: i32 = 10;
 pub const RG_OPT_SCHEDULE: i32 = 11;
 pub const RG_OPT_TILE_ROWS: i32 = 12;
 

@@ -67,7 +67,6 @@ void DeviceBuffer::release() {
 }
 void WavefrontScratch::release() {
     ray[0].release(); ray[1].release(); hit_t.release(); hit_body.release();
-    stage_ray.release(); stage_key.release(); stage_meta.release(); bins.release();
     for (int p = 0; p < 2; ++p) {
         sray[p].release(); s_tmax[p].release(); s_ab[p].release(); s_lit[p].release(); lit_bc[p].release(); lit_node[p].release();
     }
@@ -653,10 +652,6 @@ int rg_scene_set_option(rg_scene *sc, int32_t key, int64_t value) {
         case RG_OPT_GRAPH:
             if (value < 0 || value > 2) break;
             sc->graph = (int)value;
-            return RG_OK;
-        case RG_OPT_REORDER:
-            if (value < 0 || value > 2) break;
-            sc->reorder = (int)value;
             return RG_OK;
         case RG_OPT_TRACE_STATS:
             sc->trace_stats = value != 0;

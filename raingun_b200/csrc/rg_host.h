@@ -54,8 +54,6 @@ struct WavefrontScratch {
     DeviceBuffer s_lit[2];      // in_light byte per shadow ray
     DeviceBuffer lit_bc[2];     // float4 (body colour, albedo) per lit hit
     DeviceBuffer lit_node[2];   // node index per lit hit
-    DeviceBuffer stage_ray, stage_key, stage_meta;   // ray reordering: children as k_shade emits them, their bins, their parents
-    DeviceBuffer bins;                               // per level: histogram, exclusive scan, cursors (kMaxBins each)
     std::vector<DeviceBuffer> nodes;   // per level: NodeA float4 + NodeB uint4
     std::vector<cudaEvent_t> events;   // timing events of the trace launches, reused across frames
     cudaStream_t aux = nullptr;        // shadow-side stream (created on first use)
@@ -112,7 +110,6 @@ struct rg_scene {
     int overlap = 0;                       // RG_OPT_OVERLAP: 0 auto (on with the grid tracer), 1 off, 2 on
     int host_free = 0;                     // RG_OPT_HOST_FREE: 0 auto (on), 1 off (host-sized loop), 2 on
     int graph = 0;                         // RG_OPT_GRAPH: 0 auto, 1 off, 2 on
-    int reorder = 0;                       // RG_OPT_REORDER: 0 auto (on with the grid tracer), 1 off, 2 on
     bool trace_stats = false;              // RG_OPT_TRACE_STATS
     uint32_t depth_hint = 0;               // levels the ray tree of this scene has been seen to use (0 = unknown)
     bool host_free_overflowed = false;     // a level once outgrew the default queue capacity: stay with the host-sized loop

@@ -27,36 +27,6 @@ namespace rg {
 constexpr uint32_t kChildDefault = 0xFFFFFFFFu;   // child colour is scene.default_color (no node)
 enum : uint32_t { NODE_MISS = 0, NODE_DIFFUSE = 1, NODE_REFLECTING = 2, NODE_REFRACTIVE = 3 };
 
-// ---- ray reordering between levels -------------------------------------------------------------
-// Primary rays are coherent (one origin, smoothly varying directions); their children are not: after
-// one or two bounces neighbouring queue entries start anywhere and go anywhere, every lane of a warp
-// walks different cells and the trace kernels run ~3x slower per ray (measured: a shuffled level-0
-// queue costs what every deeper level costs).  So the children of a level are binned before they are
-// traced: bin = (coarse grid region of the origin, direction octant), one counting sort per level
-// (histogram in k_shade, scan, scatter).  The scatter also patches the parent's child link, so nodes,
-// hits, shadow rays and grandchildren all inherit the new order.  Results do not depend on queue order.
-constexpr uint32_t kMaxBins = 8192;
-struct BinParams {
-    uint32_t enabled;
-    uint32_t shift;          // coarse region = grid cell >> shift
-    uint32_t nx, ny, nz;     // coarse regions per axis
-    uint32_t nbins;          // nx * ny * nz * 8 <= kMaxBins
-};
-
-__device__ __forceinline__ uint32_t ray_bin(const DScene &s, const BinParams &b, const Ray &r) {
-    const GridDev &g = s.grid;
-    const float gx = ((float)(r.o.x - s.cull_ref[0]) - g.lo[0]) * g.inv_cell[0];
-    const float gy = ((float)(r.o.y - s.cull_ref[1]) - g.lo[1]) * g.inv_cell[1];
-    const float gz = ((float)(r.o.z - s.cull_ref[2]) - g.lo[2]) * g.inv_cell[2];
-    // clamp in float first (NaN -> 0 through fmaxf/fminf, far-away origins -> a border region)
-    const uint32_t cx = (uint32_t)fminf(fmaxf(gx, 0.0f), (float)(g.dim[0] - 1)) >> b.shift;
-    const uint32_t cy = (uint32_t)fminf(fmaxf(gy, 0.0f), (float)(g.dim[1] - 1)) >> b.shift;
-    const uint32_t cz = (uint32_t)fminf(fmaxf(gz, 0.0f), (float)(g.dim[2] - 1)) >> b.shift;
-    const uint32_t oct = (r.d.x < 0.0 ? 1u : 0u) | (r.d.y < 0.0 ? 2u : 0u) | (r.d.z < 0.0 ? 4u : 0u);
-    const uint32_t key = ((cz * b.ny + cy) * b.nx + cx) * 8u + oct;
-    return key < b.nbins ? key : b.nbins - 1u;
-}
-
 struct LevelBuffers {
     RayQueue cur, next, shadow;
     const double *hit_t;
@@ -78,11 +48,6 @@ struct LevelBuffers {
     uint32_t level;                  // recursion depth of this level
     uint32_t count_on_device;        // shadow rays / deepest level are counted in DCounters (host-free loop)
     uint32_t last_enqueued;          // no launch follows for this level's children (depth hint): flag them
-    // ray reordering (see k_bin_scatter): `next` is then a staging queue, and per child k_shade also leaves
-    uint32_t *next_key;              // ... its bin,
-    uint32_t *next_meta;             // ... its parent node (bit 31: it is the transmission child),
-    unsigned int *bin_count;         // ... and a histogram of the bins
-    BinParams bins;
 };
 
 // Size of a level as its kernels see it (host-sized, or read from the device and clamped to the capacity).
@@ -100,10 +65,8 @@ __device__ __forceinline__ uint32_t level_size(uint32_t n, const unsigned int *n
 // locality (queues are compacted in parent order).  Pure index permutation: results are unchanged.
 struct PixelOrder {
     uint32_t width, rows, strip;   // batch geometry
-    uint32_t mul, inv, npix;       // experiment (RG_SHUFFLE_PIXELS): i -> i * mul mod npix destroys all coherence
     // queue index -> (x, batch row)
     __device__ __forceinline__ void pixel(uint32_t i, uint32_t &x, uint32_t &r) const {
-        if (mul) i = (uint32_t)(((uint64_t)i * mul) % npix);
         const uint32_t per = strip * width, sidx = i / per, j = i - sidx * per;
         const uint32_t hs = min(strip, rows - sidx * strip);
         x = j / hs;
@@ -112,8 +75,7 @@ struct PixelOrder {
     // (x, batch row) -> queue index
     __device__ __forceinline__ uint32_t index(uint32_t x, uint32_t r) const {
         const uint32_t sidx = r / strip, hs = min(strip, rows - sidx * strip);
-        const uint32_t i = sidx * strip * width + x * hs + (r - sidx * strip);
-        return mul ? (uint32_t)(((uint64_t)i * inv) % npix) : i;
+        return sidx * strip * width + x * hs + (r - sidx * strip);
     }
 };
 
@@ -225,22 +187,10 @@ __global__ void __launch_bounds__(256) k_shade(const DScene s, const LevelBuffer
     if (want_refl) {
         child_refl = base_next + __popc(m_refl & lt);
         store_ray(lb.next, child_refl, refl);
-        if (lb.bins.enabled) {
-            const uint32_t key = ray_bin(s, lb.bins, refl);
-            lb.next_key[child_refl] = key;
-            lb.next_meta[child_refl] = i;
-            atomicAdd(&lb.bin_count[key], 1u);
-        }
     }
     if (want_trans) {
         child_trans = base_next + __popc(m_refl) + __popc(m_trans & lt);
         store_ray(lb.next, child_trans, trans);
-        if (lb.bins.enabled) {
-            const uint32_t key = ray_bin(s, lb.bins, trans);
-            lb.next_key[child_trans] = key;
-            lb.next_meta[child_trans] = i | 0x80000000u;
-            atomicAdd(&lb.bin_count[key], 1u);
-        }
     }
     if (want_lit) {
         // shade_diffuse's per-light setup (rendering.rs:141-149,163): shadow ray from
@@ -314,53 +264,6 @@ __global__ void __launch_bounds__(256) k_combine(const DScene s, float4 *node_a,
     }
     a.x = out.r; a.y = out.g; a.z = out.b;
     node_a[i] = a;
-    }
-}
-
-// exclusive prefix sum of the bin histogram (<= kMaxBins entries): one 1024-thread block
-__global__ void __launch_bounds__(1024) k_bin_scan(const unsigned int *__restrict__ count, unsigned int *base, uint32_t nbins) {
-    __shared__ uint32_t part[1024];
-    const uint32_t t = threadIdx.x, per = (nbins + 1023u) / 1024u;
-    const uint32_t lo = min(nbins, t * per), hi = min(nbins, lo + per);
-    uint32_t sum = 0;
-    for (uint32_t k = lo; k < hi; ++k) sum += count[k];
-    part[t] = sum;
-    __syncthreads();
-    for (uint32_t off = 1; off < 1024u; off <<= 1) {
-        const uint32_t v = t >= off ? part[t - off] : 0u;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    uint32_t run = t ? part[t - 1] : 0u;
-    for (uint32_t k = lo; k < hi; ++k) { base[k] = run; run += count[k]; }
-}
-
-// moves every staged child to its place in the binned queue and tells its parent where it went
-__global__ void __launch_bounds__(256) k_bin_scatter(const RayQueue staged, const RayQueue sorted, const uint32_t *__restrict__ key,
-                                                     const uint32_t *__restrict__ meta, const unsigned int *__restrict__ base,
-                                                     unsigned int *cursor, uint4 *parent_b, uint32_t cap,
-                                                     const unsigned int *n_dev, const unsigned int *void_flag) {
-    const uint32_t n = level_size(cap, n_dev, void_flag);
-    const uint32_t lane = threadIdx.x & 31u;
-    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {
-        const uint32_t i = i0 + lane;
-        const bool have = i < n;
-        const uint32_t k = have ? key[i] : 0xFFFFFFFFu;
-        // one atomic per distinct bin of the warp (neighbours mostly share a bin)
-        const uint32_t peers = __match_any_sync(0xffffffffu, k);
-        const uint32_t leader = __ffs(peers) - 1u;
-        uint32_t first = 0;
-        if (have && lane == leader) first = atomicAdd(&cursor[k], (unsigned)__popc(peers));
-        first = __shfl_sync(0xffffffffu, first, leader);
-        if (have) {
-            const uint32_t pos = base[k] + first + __popc(peers & ((1u << lane) - 1u));
-            const double2 a = staged.a[i], b = staged.b[i], c = staged.c[i];
-            sorted.a[pos] = a; sorted.b[pos] = b; sorted.c[pos] = c;
-            const uint32_t m = meta[i];
-            uint32_t *link = reinterpret_cast<uint32_t *>(parent_b + (m & 0x7FFFFFFFu));
-            link[m >> 31] = pos;   // .x = reflection child, .y = transmission child
-        }
     }
 }
 
@@ -465,19 +368,6 @@ static PixelOrder pixel_order(uint32_t width, uint32_t rows) {
     po.width = width;
     po.rows = rows;
     po.strip = strip;
-    po.mul = po.inv = 0;
-    po.npix = width * rows;
-    static const bool shuffle = [] { const char *e = getenv("RG_SHUFFLE_PIXELS"); return e && atoi(e) != 0; }();
-    if (shuffle && po.npix > 2) {   // a multiplier coprime to npix and its modular inverse (extended Euclid)
-        uint64_t m = 2654435761ull % po.npix;
-        auto gcd = [](uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; };
-        while (m < 2 || gcd(m, po.npix) != 1) ++m;
-        long long t = 0, nt = 1, r = po.npix, nr = (long long)m;
-        while (nr) { long long q = r / nr, tt = t - q * nt; t = nt; nt = tt; long long rr = r - q * nr; r = nr; nr = rr; }
-        if (t < 0) t += po.npix;
-        po.mul = (uint32_t)m;
-        po.inv = (uint32_t)t;
-    }
     return po;
 }
 
@@ -819,27 +709,7 @@ constexpr uint32_t kLevelGrowth = 2;
 struct DevPlan {
     uint32_t levels = 0;                    // levels 0 .. levels-1 are enqueued
     uint32_t cap[RG_MAX_DEPTH + 2] = {0};
-    BinParams bins{};                       // ray reordering between levels (grid tracer only)
 };
-
-// RG_OPT_REORDER: 0 = automatic (on with the grid tracer), 1 = off, 2 = on
-static BinParams bin_params(const rg_scene *sc, bool use_grid) {
-    BinParams b{};
-    static const int env = [] { const char *e = getenv("RG_REORDER"); return e ? atoi(e) : -1; }();
-    const int mode = env >= 0 ? env : sc->reorder;
-    const GridDev &g = sc->ds.grid;
-    if (mode != 2 || !use_grid || !g.enabled) return b;   // measured: bins of this coarseness buy ~6 % on the traces and cost more than that
-    static const uint32_t max_regions = [] { const char *e = getenv("RG_REORDER_REGIONS"); const int v = e ? atoi(e) : 0; return (uint32_t)(v > 0 ? v : (int)(kMaxBins / 8)); }();
-    for (uint32_t shift = 0; shift < 9; ++shift) {
-        const uint32_t nx = ((uint32_t)g.dim[0] + (1u << shift) - 1) >> shift, ny = ((uint32_t)g.dim[1] + (1u << shift) - 1) >> shift,
-                       nz = ((uint32_t)g.dim[2] + (1u << shift) - 1) >> shift;
-        if ((uint64_t)nx * ny * nz <= std::min<uint32_t>(max_regions, kMaxBins / 8)) {
-            b.enabled = 1; b.shift = shift; b.nx = nx; b.ny = ny; b.nz = nz; b.nbins = nx * ny * nz * 8u;
-            break;
-        }
-    }
-    return b;
-}
 
 static int plan_batch_dev(rg_scene *sc, uint32_t npix, DevPlan &plan, bool use_grid) {
     const DScene &ds = sc->ds;
@@ -878,14 +748,6 @@ static int plan_batch_dev(rg_scene *sc, uint32_t npix, DevPlan &plan, bool use_g
         if ((rc = wf.lit_bc[p].reserve((size_t)c * 16))) return rc;
         if ((rc = wf.lit_node[p].reserve((size_t)c * 4))) return rc;
     }
-    plan.bins = bin_params(sc, use_grid);
-    if (plan.bins.enabled && plan.levels > 1) {
-        const uint64_t c = std::max<uint64_t>(std::max(cap_max[0], cap_max[1]), 1);
-        if ((rc = wf.stage_ray.reserve((size_t)c * 48))) return rc;
-        if ((rc = wf.stage_key.reserve((size_t)c * 4))) return rc;
-        if ((rc = wf.stage_meta.reserve((size_t)c * 4))) return rc;
-        if ((rc = wf.bins.reserve((size_t)plan.levels * 3 * kMaxBins * sizeof(unsigned int)))) return rc;
-    }
     return RG_OK;
 }
 
@@ -904,12 +766,12 @@ static int enqueue_batch_dev(rg_scene *sc, const DevPlan &plan, uint32_t width, 
     const unsigned max_blocks = (unsigned)sc->sm_count * 16u;
     auto blocks = [&](uint64_t n) { return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, max_blocks)); };
     const bool overlap = L > 0 && (sc->overlap == 2 || (sc->overlap == 0 && use_grid));
+    // the shadow side of a level runs beside the path side of the next levels, on one auxiliary stream (a second
+    // one for the odd levels, so that two shadow sides overlap as well, was measured: no gain at any batch size)
     cudaStream_t aux = overlap ? wf.aux : stream;
     cudaEvent_t shadow_done[2] = {nullptr, nullptr};
 
     RG_CUDA(cudaMemsetAsync(dc->lvl, 0, sizeof(dc->lvl), stream));
-    const bool reorder = plan.bins.enabled && plan.levels > 1;
-    if (reorder) RG_CUDA(cudaMemsetAsync(wf.bins.ptr, 0, (size_t)plan.levels * 3 * kMaxBins * sizeof(unsigned int), stream));
     RayQueue cur = make_queue(wf.ray[0], plan.cap[0]);
     const PixelOrder po = pixel_order(width, npix / width);
     k_generate<<<(npix + 255) / 256, 256, 0, stream>>>(ds, cur, width, height, y0, npix, d_rows, &dc->lvl[0].n, po);
@@ -963,31 +825,10 @@ static int enqueue_batch_dev(rg_scene *sc, const DevPlan &plan, uint32_t width, 
         lb.level = d;
         lb.count_on_device = 1u;
         lb.last_enqueued = (d + 1 == plan.levels && can_spawn) ? 1u : 0u;
-        const RayQueue next_sorted = lb.next;
-        unsigned int *bin_count = nullptr, *bin_base = nullptr, *bin_cursor = nullptr;
-        const bool bin_this = reorder && can_spawn;
-        if (bin_this) {   // children are staged, then moved to their bins (k_bin_scatter)
-            bin_count = wf.bins.as<unsigned int>() + (size_t)d * 3 * kMaxBins;
-            bin_base = bin_count + kMaxBins;
-            bin_cursor = bin_base + kMaxBins;
-            lb.next = make_queue(wf.stage_ray, std::max<uint32_t>(cap_next, 1u));
-            lb.next_key = wf.stage_key.as<uint32_t>();
-            lb.next_meta = wf.stage_meta.as<uint32_t>();
-            lb.bin_count = bin_count;
-            lb.bins = plan.bins;
-        }
         if (shadow_done[p]) RG_CUDA(cudaStreamWaitEvent(stream, shadow_done[p], 0));   // level d-2 still reads these buffers
         k_shade<<<blocks(cap), 256, 0, stream>>>(ds, lb, dc);
         RG_CUDA(cudaGetLastError());
         st->gpu_launches++;
-        if (bin_this) {
-            k_bin_scan<<<1, 1024, 0, stream>>>(bin_count, bin_base, plan.bins.nbins);
-            k_bin_scatter<<<blocks(cap_next), 256, 0, stream>>>(lb.next, next_sorted, lb.next_key, lb.next_meta, bin_base, bin_cursor,
-                                                              lb.node_b, cap_next, &dc->lvl[d + 1].n, &dc->overflow);
-            RG_CUDA(cudaGetLastError());
-            st->gpu_launches += 2;
-            lb.next = next_sorted;
-        }
 
         if (L) {   // shadow side, concurrent with the next level's path side
             if (overlap) {
@@ -1051,9 +892,9 @@ static std::vector<uint64_t> graph_key(const rg_scene *sc, const DevPlan &plan, 
     const WavefrontScratch &wf = sc->wf;
     std::vector<uint64_t> k = {width, height, y0, npix, (uint64_t)(uintptr_t)d_rows, (uint64_t)(uintptr_t)d_out,
                                (uint64_t)use_grid, (uint64_t)sc->scatter_out | ((uint64_t)sc->out_f32 << 1), (uint64_t)sc->ds.max_depth, (uint64_t)sc->overlap,
-                               (uint64_t)sc->verify_cull, (uint64_t)sc->trace_stats, (uint64_t)plan.levels, (uint64_t)plan.bins.nbins};
+                               (uint64_t)sc->verify_cull, (uint64_t)sc->trace_stats, (uint64_t)plan.levels};
     auto add = [&](const DeviceBuffer &b) { k.push_back((uint64_t)(uintptr_t)b.ptr); };
-    add(wf.ray[0]); add(wf.ray[1]); add(wf.hit_t); add(wf.hit_body); add(wf.stage_ray); add(wf.stage_key); add(wf.stage_meta); add(wf.bins);
+    add(wf.ray[0]); add(wf.ray[1]); add(wf.hit_t); add(wf.hit_body);
     for (int p = 0; p < 2; ++p) { add(wf.sray[p]); add(wf.s_tmax[p]); add(wf.s_ab[p]); add(wf.s_lit[p]); add(wf.lit_bc[p]); add(wf.lit_node[p]); }
     for (uint32_t d = 0; d < plan.levels; ++d) add(wf.nodes[d]);
     return k;
@@ -1149,8 +990,9 @@ int wavefront_render(rg_scene *sc, uint32_t width, uint32_t height, uint32_t y0,
         RG_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(DCounters), stream));
         RG_CUDA(cudaEventRecord(sc->ev[0], stream));
         int rc = RG_OK;
-        if (host_free && sc->ds.n_lights > 0 && (sc->overlap == 2 || (sc->overlap == 0 && use_grid)) && !sc->wf.aux)
-            RG_CUDA(cudaStreamCreateWithFlags(&sc->wf.aux, cudaStreamNonBlocking));
+        if (host_free && sc->ds.n_lights > 0 && (sc->overlap == 2 || (sc->overlap == 0 && use_grid))) {
+            if (!sc->wf.aux) RG_CUDA(cudaStreamCreateWithFlags(&sc->wf.aux, cudaStreamNonBlocking));
+        }
         for (uint32_t y = y0; y < y1 && rc == RG_OK;) {
             const uint32_t ye = (uint32_t)std::min<uint64_t>((uint64_t)y + batch_rows, y1);
             // RGBA8: 4 bytes per pixel; f32 colours (rg_render_rows_f32): 12

@@ -10,7 +10,11 @@ for n in $1; do
 import json
 try:
     d=json.loads(open("gpurun_out/scale_$n.json").read().strip().splitlines()[-1])
-    print("N=$n value %.1f Mrays/s  %.2f ms/frame | e2e %.1f Mrays/s %.2f ms | launches %d | %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["e2e"]["ms_per_step"], d["gpu_launches"], d["config"]["parallelism"]))
+    print("N=$n value %.1f Mrays/s  %.2f ms/frame | e2e %.1f Mrays/s %.2f ms (upload %.2f) | launches %d | %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["e2e"]["ms_per_step"], d["e2e"]["scene_upload_ms_per_step"], d["gpu_launches"], d["config"]["parallelism"]))
+    il = d.get("in_library_multi_gpu")
+    if il: print("      in-library: static %.2f ms/frame, steal %.2f ms/frame" % (il["static"]["ms_per_frame"], il["steal"]["ms_per_frame"]))
+    c5 = (d.get("configs") or {}).get("C5@7680x4320")
+    if c5: print("      C5: 1 GPU %.1f ms" % c5["ms_per_frame"], ("| sharded x%d %.1f ms" % (c5["sharded"]["n_gpus"], c5["sharded"]["ms_per_frame_wall_incl_d2h"])) if "sharded" in c5 else "")
 except Exception as e:
     print("N=$n ERR", e); print(open("gpurun_out/scale_$n.err").read()[-1500:])
 PY
