@@ -38,6 +38,15 @@ impl Drop for B200Scene {
 /// Flattens `Vec<Body>` / `Vec<Light>` body by body, IN ORDER (the order is the tie-break of
 /// `Scene::trace`, scene.rs:34-39), and uploads.  f32 fields are passed through as stored.
 pub fn upload(scene: &Scene) -> B200Scene {
+    let device = match ::std::env::var("RAINGUN_DEVICE") {
+        Ok(v) => v.parse::<i32>().unwrap_or(sys::RG_DEVICE_ALL),
+        Err(_) => sys::RG_DEVICE_ALL,
+    };
+    upload_on(scene, device)
+}
+
+/// The same on one named device (or `RG_DEVICE_ALL`).
+pub fn upload_on(scene: &Scene, device: i32) -> B200Scene {
     let n = scene.bodies.len();
     let mut kind = vec![0u8; n];
     let mut geom = vec![0f64; 8 * n];
@@ -154,7 +163,9 @@ pub fn upload(scene: &Scene) -> B200Scene {
         textures: if textures.is_empty() { ::std::ptr::null() } else { textures.as_ptr() },
     };
     let mut handle = ::std::ptr::null_mut();
-    let rc = unsafe { sys::rg_scene_create(&desc, 0, &mut handle) };   // the library copies everything
+    // RG_DEVICE_ALL: every visible GPU; the library splits a render into row tiles across them itself
+    // (rayon's par_iter over the machine's cores, rendering.rs:27-35).
+    let rc = unsafe { sys::rg_scene_create(&desc, device, &mut handle) };   // the library copies everything
     assert!(rc == sys::RG_OK, "raingun_b200: {}", last_error());         // the reference panics on failure too
     B200Scene(handle)
 }
@@ -168,14 +179,14 @@ pub fn render_image(scene: &Scene, width: u32, height: u32) -> ImageBuffer<Rgba<
     ImageBuffer::from_raw(width, height, raw).unwrap()                   // rendering.rs:37
 }
 
-extern "C" fn on_rows(y0: u32, rows: u32, width: u32, rgba: *const u8, user: *mut c_void) -> c_int {
+extern "C" fn on_rows(y0: u32, rows: u32, width: u32, rgb: *const f32, user: *mut c_void) -> c_int {
     let tx = unsafe { &*(user as *const Sender<RenderedPixel>) };
-    let px = unsafe { ::std::slice::from_raw_parts(rgba, (rows * width * 4) as usize) };
-    for (i, p) in px.chunks(4).enumerate() {
+    let px = unsafe { ::std::slice::from_raw_parts(rgb, (rows * width * 3) as usize) };
+    for (i, p) in px.chunks(3).enumerate() {
         let (x, y) = (i as u32 % width, y0 + i as u32 / width);
-        // the reference sends unquantised colours and the collector quantises (src/render.rs:204-208);
-        // from_rgba(b).rgba() is the identity on bytes, so the preview image is unchanged
-        let color = Color::from_rgba(Rgba { data: [p[0], p[1], p[2], p[3]] });
+        // RenderedPixel.color is the UNQUANTISED f32 colour (rendering.rs:18-22,59-65): rg_render_stream_f32
+        // delivers the reference's own f32 bits, so any consumer of the channel sees what it would have seen
+        let color = Color { red: p[0], green: p[1], blue: p[2] };
         if tx.send(RenderedPixel { x: x, y: y, color: color }).is_err() {
             return 1;                                                    // closed channel: rendering.rs:53-54,67
         }
@@ -185,10 +196,11 @@ extern "C" fn on_rows(y0: u32, rows: u32, width: u32, rgba: *const u8, user: *mu
 
 /// Scene::streaming_render (scene.rs:45-51 -> rendering.rs:40-69).
 pub fn streaming_render(scene: &Scene, width: u32, height: u32, channel_tx: Sender<RenderedPixel>) {
-    let gpu = upload(scene);
+    // the f32 stream is a single-device entry point: one GPU renders the bands
+    let gpu = upload_on(scene, 0);
     let rc = unsafe {
-        sys::rg_render_stream(gpu.0, width, height, 0, on_rows, &channel_tx as *const _ as *mut c_void,
-                              ::std::ptr::null_mut())
+        sys::rg_render_stream_f32(gpu.0, width, height, 0, on_rows, &channel_tx as *const _ as *mut c_void,
+                                  ::std::ptr::null_mut())
     };
     assert!(rc == sys::RG_OK || rc == sys::RG_E_CANCELLED, "raingun_b200: {}", last_error());
 }
