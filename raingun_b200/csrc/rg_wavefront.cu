@@ -94,7 +94,10 @@ __global__ void __launch_bounds__(256) k_generate(const DScene s, RayQueue q, ui
     store_ray(q, i, create_prime(s, x, y, width, height));
 }
 
-__global__ void __launch_bounds__(256) k_shade(const DScene s, const LevelBuffers lb, DCounters *ctr) {
+#ifndef RG_SHADE_MINB
+#define RG_SHADE_MINB 4   // 64 registers: the kernel waits on gathers (long scoreboard), occupancy pays (measured 3 / 4 / 5 CTAs per SM)
+#endif
+__global__ void __launch_bounds__(256, RG_SHADE_MINB) k_shade(const DScene s, const LevelBuffers lb, DCounters *ctr) {
     const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     const uint32_t n_level = level_size(lb.n, lb.n_dev, lb.void_flag);
     if (lb.count_on_device && blockIdx.x == 0 && threadIdx.x == 0 && n_level) atomicMax(&ctr->max_level, lb.level);
@@ -195,7 +198,9 @@ __global__ void __launch_bounds__(256) k_shade(const DScene s, const LevelBuffer
     if (want_lit) {
         // shade_diffuse's per-light setup (rendering.rs:141-149,163): shadow ray from
         // hit_point + n * SHADOW_BIAS towards the light; the light-dependent scalars are kept
-        // for k_diffuse.
+        // for k_diffuse.  (Doing this warp-cooperatively — one (hit, light) pair per lane instead of a
+        // per-light loop in the ~third of the lanes that are lit — was measured: no gain once the kernel
+        // runs at 64 registers; it waits on gathers, not on issue slots.)
         const uint32_t j = base_lit + __popc(m_lit & lt);
         lb.lit_node[j] = i;
         lb.lit_bc[j] = make_float4(bc.r, bc.g, bc.b, s.mat[body].albedo);
