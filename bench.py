@@ -243,6 +243,14 @@ def grid_issue_roofline(rg, _native, data, w, h, staging, sptr, local_rank, valu
     sc.set_option(_native.OPT_TRACE_STATS, 1)
     st = sc.render_rows_device(w, h, 0, h, staging.data_ptr(), sptr)
     sc.close()
+    # the kernel's own launch durations, measured live: one stream, eager launches, CUDA events around every trace launch
+    sc = rg.Scene(data, device=local_rank)
+    sc.set_option(_native.OPT_OVERLAP, 1)
+    sc.set_option(_native.OPT_GRAPH, 1)
+    kt = None
+    for _ in range(3):
+        kt = sc.render_rows_device(w, h, 0, h, staging.data_ptr(), sptr)
+    sc.close()
     r = max(1, st.rays)
     tipr, src, prof = profiled_thread_instructions()
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
@@ -255,10 +263,17 @@ def grid_issue_roofline(rg, _native, data, w, h, staging, sptr, local_rank, valu
                        "l2_bytes_algorithmic": 48.0 * st.grid_cells / r + 48.0 + 12.0},
            "per_ray_note": "l2_bytes_algorithmic = 48 B per cell visited (chained records of crowded cells add a few per cent) "
                            "+ 48 B ray + 12 B hit"}
-    if tipr:
-        achieved = tipr * value_mrays * 1e6
-        out.update({"achieved": achieved / 1e12, "frac": achieved / peak, "thread_instr_per_ray": tipr, "thread_instr_source": f"profiles/{src}",
-                    "ipc_over_4_times_lanes_over_32": (prof or {}).get("ipc_lanes_product")})
+    if tipr and kt and kt.ms_trace > 0:
+        launches = 2 * (kt.max_level + 1)
+        achieved = tipr * kt.rays / (kt.ms_trace * 1e-3)        # thread instructions / second while the kernel runs
+        out.update({"achieved": achieved / 1e12, "frac": achieved / peak,
+                    "kernel_ms_per_frame": kt.ms_trace, "launches_per_frame": launches, "avg_launch_ms": kt.ms_trace / max(1, launches),
+                    "thread_instr_per_ray": tipr, "thread_instr_source": f"profiles/{src}",
+                    "frac_under_ncu": (prof or {}).get("ipc_lanes_product"), "avg_active_lanes_under_ncu": (prof or {}).get("avg_active_lanes"),
+                    # the same numerator against the WHOLE step (k_shade etc. included, streams overlapped): what the frame leaves unused
+                    "frac_of_step": tipr * value_mrays * 1e6 / peak,
+                    "how": "achieved = thread instructions per ray (ncu, committed capture) x rays of the frame / sum of the trace launches' "
+                           "durations (CUDA events, one stream, this run)"})
     return out
 
 

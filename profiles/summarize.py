@@ -56,12 +56,55 @@ def launch_summary(tag, lines):
         a[0] += 1
         a[1] += ms
         total += ms
-    lines.append(f"## Launch list (`launches_{tag}.csv`, whole `bench.py --steps 2 --warmup 1 --no-cpu-baseline` run)\n")
+    lines.append(f"## Launch list (`launches_{tag}.csv`, whole `bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-configs` run)\n")
     lines.append("The run contains the grid-accelerated arm (value + e2e), the brute-force roofline arm and the\n"
                  "FMA-peak microbenchmarks; shares are of the summed kernel time of the whole run.\n")
     lines.append("| kernel | launches | total ms | share |\n|---|---:|---:|---:|")
     for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append(f"| `{k}` | {n} | {ms:.3f} | {100 * ms / total:.1f} % |")
+    lines.append("")
+
+
+def grid_counters(tag, lines):
+    """Instruction counters of every k_trace_grid launch of two C4 frames -> <tag>_grid_counters.json: the numerator of the
+    lane-issue roofline bench.py reports (thread instructions per ray) and the IPC x lanes product under ncu."""
+    import json
+    path = os.path.join(OUT, f"gridcounters_{tag}.csv")
+    if not os.path.exists(path):
+        return
+    shutil.copy(path, os.path.join(HERE, f"{tag}_gridcounters.csv"))
+    rows = list(csv.DictReader([l for l in open(path) if not l.startswith("==")]))
+    per = collections.OrderedDict()
+    for r in rows:
+        d = per.setdefault(r["ID"], {"name": re.sub(r"\(.*", "", r["Kernel Name"])})
+        d[r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
+        d[r["Metric Name"] + "/unit"] = r["Metric Unit"]
+    launches = list(per.values())
+    half = len(launches) // 2          # two identical frames were captured: use the second (warm)
+    frame = launches[half:] if half else launches
+    to_ns = lambda d: d["gpu__time_duration.sum"] * {"ns": 1.0, "us": 1e3, "ms": 1e6}.get(d.get("gpu__time_duration.sum/unit", "ns"), 1.0)
+    thread_inst = sum(d["smsp__thread_inst_executed.sum"] for d in frame)
+    warp_inst = sum(d["smsp__inst_executed.sum"] for d in frame)
+    ns = sum(to_ns(d) for d in frame)
+    rays = 111009057   # C4 at 3840x2160: every Scene::trace call of the frame goes through one of these launches
+    peak_per_ns = 148 * 4 * 32 * 1.965   # thread instructions per ns at 1965 MHz
+    out = {"workload": "C4 3840x2160 (tools/prof_grid.py, host-sized loop: every launch exactly sized)", "launches": len(frame),
+           "rays": rays, "thread_inst": thread_inst, "warp_inst": warp_inst, "thread_inst_per_ray": thread_inst / rays,
+           "warp_inst_per_ray": warp_inst / rays, "avg_active_lanes": thread_inst / warp_inst,
+           "sum_kernel_ms_under_ncu": ns * 1e-6, "ipc_lanes_product": thread_inst / (ns * peak_per_ns),
+           "note": "ipc_lanes_product = thread instructions / (kernel time under ncu x 148 SM x 4 x 32 x 1.965 GHz) = IPC/4 x lanes/32, "
+                   "serialised and cold-cache; bench.py multiplies thread_inst_per_ray by the rays/s it measures"}
+    with open(os.path.join(HERE, f"{tag}_grid_counters.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    lines.append(f"## Instruction counters of `k_trace_grid` over one C4 frame (`{tag}_gridcounters.csv`)\n")
+    lines.append(f"- launches {len(frame)}, rays {rays}: **{out['thread_inst_per_ray']:.0f} thread instructions per ray**, "
+                 f"{out['warp_inst_per_ray']:.1f} warp instructions per ray, {out['avg_active_lanes']:.1f} of 32 lanes active on average")
+    lines.append(f"- lane-issue utilisation under ncu (IPC/4 x lanes/32): **{out['ipc_lanes_product']:.3f}** "
+                 f"(sum of kernel times {out['sum_kernel_ms_under_ncu']:.2f} ms, serialised)")
+    lines.append("| launch | kernel | ms | warp instr | lanes | IPC |\n|---:|---|---:|---:|---:|---:|")
+    for k, d in enumerate(frame):
+        lines.append(f"| {k} | `{d['name']}` | {to_ns(d) * 1e-6:.3f} | {d['smsp__inst_executed.sum']:.3g} | "
+                     f"{d.get('smsp__thread_inst_executed_per_inst_executed.ratio', 0):.1f} | {d.get('sm__inst_executed.avg.per_cycle_active', 0):.2f} |")
     lines.append("")
 
 
@@ -125,6 +168,7 @@ def main():
              "same command without ncu and requires exit 0).  Absolute times under ncu are cold-cache and\n"
              "serialised; bench.py's CUDA-event numbers are the timings of record.\n"]
     launch_summary(tag, lines)
+    grid_counters(tag, lines)
     for rep in sorted(f for f in os.listdir(OUT) if f.endswith(f"_{tag}.ncu-rep")):
         path = os.path.join(OUT, rep)
         lines.append(f"## `--set full` capture `{rep}`\n")
