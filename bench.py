@@ -472,6 +472,19 @@ def main() -> int:
             gather_note = gather_note or "peer gather unavailable on another rank"
             print(f"[bench] {gather_note}; using the NCCL reduce gather", file=sys.stderr, flush=True)
 
+    host_barrier = None
+    if world > 1:   # end-of-frame barrier of the ranks in shared memory (microseconds) instead of a GPU collective
+        from raingun_b200.dist import HostBarrier
+        try:
+            host_barrier = HostBarrier(rank, world, tag="bench")
+        except Exception as e:
+            print(f"[bench] shared-memory barrier unavailable on rank {rank}: {e}", file=sys.stderr, flush=True)
+        ok = torch.tensor([0 if host_barrier is None else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0 and host_barrier is not None:
+            host_barrier.close()
+            host_barrier = None
+
     def lane_renderers(lanes):
         if peer_frames is not None:
             return [(lambda rows, fptr, sc_=sc_, st_=st_: sc_.render_rowlist_scatter(w, h, rows, fptr, st_))
@@ -496,7 +509,7 @@ def main() -> int:
         res = render_frame_sharded(
             lane_renderers(lanes_), w, h, rank, world,
             frame_counter[0], device, tile_rows=args.tile_rows, schedule=args.schedule, staging=staging,
-            gather_mode=args.gather, frame_buf=frame_buf, lead=args.lead, peer_frames=peer_frames)
+            gather_mode=args.gather, frame_buf=frame_buf, lead=args.lead, peer_frames=peer_frames, host_barrier=host_barrier)
         gathered["frame"] = res.frame   # rank 0: the gathered (H, W, 4) frame in HBM
         gathered["schedule"] = res.schedule
         return (sum(s.rays for s in res.stats), sum(s.gpu_launches for s in res.stats),
@@ -579,7 +592,7 @@ def main() -> int:
             frame_counter[0] += 1
             res = render_frame_sharded(
                 [lambda rows, fptr, sc_=sc: sc_.render_rowlist_host(w, h, rows, fptr)], w, h, rank, world, frame_counter[0], device,
-                tile_rows=args.tile_rows, schedule=args.schedule, gather_mode="host", peer_frames=host_frames)
+                tile_rows=args.tile_rows, schedule=args.schedule, gather_mode="host", peer_frames=host_frames, host_barrier=host_barrier)
             gathered["host_frame"] = res.frame
             r = sum(s_.rays for s_ in res.stats)
             sc.close()
@@ -721,7 +734,7 @@ def main() -> int:
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.workload, spec, data, {
                 "accel": accel_used, "pipeline": "wavefront",
-                "parallelism": f"row-tiles x{world} ({args.schedule}->{gathered.get('schedule', '?')}, {args.tile_rows}-row tiles, {inflight} batches in flight per GPU, gather={args.gather})" if world > 1 else "1 GPU",
+                "parallelism": f"row-tiles x{world} ({args.schedule}->{gathered.get('schedule', '?')}, {args.tile_rows}-row tiles, {inflight} batches in flight per GPU, gather={args.gather}, end-of-frame barrier={'shared memory' if host_barrier is not None else 'nccl'})" if world > 1 else "1 GPU",
                 "l2": "per-frame working set (ray queues + nodes, several GB) exceeds the 126 MB L2; no explicit flush"}),
             "rays_per_frame": rays // max(1, args.steps),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": desc_bytes * world * inflight,
@@ -744,6 +757,8 @@ def main() -> int:
         print(json.dumps(line), flush=True)
     if peer_frames is not None:
         peer_frames.close()
+    if host_barrier is not None:
+        host_barrier.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -260,6 +260,15 @@ int rg_host_unregister(void *ptr);
  * can write its rows into a frame on another.  Harmless if already enabled. */
 int rg_device_enable_peer(int32_t device, int32_t peer);
 
+/* A barrier for the processes of one box (one per GPU) in POSIX shared memory: the creator (create = 1) makes
+ * it for `parties` processes and hands `name` ("/something") to the others by any channel; every process then
+ * calls rg_shm_barrier_wait at the end of a sharded frame.  Each rank has synchronised its own stream by then
+ * (the render calls block), so a sense-reversing counter does in microseconds what a GPU collective does in
+ * 60-100 us.  Close in every process; the creator also unlinks the name. */
+int rg_shm_barrier_open(const char *name, uint32_t parties, int32_t create, void **handle);
+int rg_shm_barrier_wait(void *handle);
+int rg_shm_barrier_close(void *handle);
+
 /* A device frame that other PROCESSES (one per GPU) can map: create on the owning rank, pass the
  * opaque handle bytes to the others (any channel), open there.  Close with is_owner = 1 on the
  * creating rank (frees the memory), 0 elsewhere (unmaps). */

@@ -144,6 +144,9 @@ extern "C" {
     pub fn rg_host_register(ptr: *mut c_void, bytes: usize) -> c_int;
     pub fn rg_host_unregister(ptr: *mut c_void) -> c_int;
     pub fn rg_device_enable_peer(device: i32, peer: i32) -> c_int;
+    pub fn rg_shm_barrier_open(name: *const c_char, parties: u32, create: i32, handle: *mut *mut c_void) -> c_int;
+    pub fn rg_shm_barrier_wait(handle: *mut c_void) -> c_int;
+    pub fn rg_shm_barrier_close(handle: *mut c_void) -> c_int;
     pub fn rg_shared_frame_create(device: i32, bytes: usize, d_ptr: *mut *mut c_void, handle: *mut u8) -> c_int;
     pub fn rg_shared_frame_open(device: i32, handle: *const u8, d_ptr: *mut *mut c_void) -> c_int;
     pub fn rg_shared_frame_close(device: i32, d_ptr: *mut c_void, is_owner: i32) -> c_int;

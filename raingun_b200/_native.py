@@ -34,7 +34,7 @@ ROWS_F32_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, c
 
 # every symbol include/raingun_b200.h declares
 EXPORTS = ("rg_scene_create", "rg_scene_create_multi", "rg_scene_device_count", "rg_scene_destroy", "rg_scene_set_option", "rg_render", "rg_render_rows",
-           "rg_render_rows_device", "rg_render_rowlist_device", "rg_render_rowlist_scatter", "rg_render_rowlist_host", "rg_host_register", "rg_host_unregister", "rg_device_enable_peer", "rg_shared_frame_create",
+           "rg_render_rows_device", "rg_render_rowlist_device", "rg_render_rowlist_scatter", "rg_render_rowlist_host", "rg_host_register", "rg_host_unregister", "rg_device_enable_peer", "rg_shm_barrier_open", "rg_shm_barrier_wait", "rg_shm_barrier_close", "rg_shared_frame_create",
            "rg_shared_frame_open", "rg_shared_frame_close", "rg_render_stream", "rg_render_rows_f32", "rg_render_stream_f32", "rg_trim", "rg_last_error", "rg_measure_peaks",
            "rg_device_count")
 IPC_HANDLE_BYTES = 64
@@ -84,6 +84,12 @@ def lib() -> ctypes.CDLL:
     L.rg_host_register.argtypes = [vp, ctypes.c_size_t]
     L.rg_host_unregister.restype = ctypes.c_int
     L.rg_host_unregister.argtypes = [vp]
+    L.rg_shm_barrier_open.restype = ctypes.c_int
+    L.rg_shm_barrier_open.argtypes = [ctypes.c_char_p, u32, i32, ctypes.POINTER(vp)]
+    L.rg_shm_barrier_wait.restype = ctypes.c_int
+    L.rg_shm_barrier_wait.argtypes = [vp]
+    L.rg_shm_barrier_close.restype = ctypes.c_int
+    L.rg_shm_barrier_close.argtypes = [vp]
     L.rg_device_enable_peer.restype = ctypes.c_int
     L.rg_device_enable_peer.argtypes = [i32, i32]
     L.rg_shared_frame_create.restype = ctypes.c_int

@@ -316,18 +316,12 @@ static int build_scene(rg_scene *sc, const rg_scene_desc *d) {
         fprintf(stderr, "[build_scene] %-14s %.3f ms\n", what, std::chrono::duration<double, std::milli>(t - T0).count());
         T0 = t;
     };
-    uint32_t ns = 0;
-    for (uint32_t i = 0; i < n; ++i) ns += d->body_kind[i] == RG_BODY_SPHERE ? 1u : 0u;
-    const uint32_t nm = n - ns;
-    ds.n_spheres = ns;
-    ds.n_misc = nm;
-    const size_t cull_padded = ((size_t)ns + 3) / 4 * 4;
-
     // ---- everything the device needs from the host, laid out in ONE pinned staging buffer -> one async copy
+    // (the sphere / non-sphere lists are laid out for the worst case, so that one pass over the bodies fills everything)
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t off_kind = 0, off_geom = align(off_kind + n), off_mat = align(off_geom + (size_t)n * 64),
-                 off_sph = align(off_mat + (size_t)n * sizeof(BodyMat)), off_sphb = align(off_sph + (size_t)ns * 32),
-                 off_misc = align(off_sphb + (size_t)ns * 4), total = align(off_misc + (size_t)nm * 4);
+                 off_sph = align(off_mat + (size_t)n * sizeof(BodyMat)), off_sphb = align(off_sph + (size_t)n * 32),
+                 off_misc = align(off_sphb + (size_t)n * 4), total = align(off_misc + (size_t)n * 4);
     if (sc->h_stage_cap < total) {
         if (sc->h_stage) cudaFreeHost(sc->h_stage);
         sc->h_stage = nullptr;
@@ -346,10 +340,10 @@ static int build_scene(rg_scene *sc, const rg_scene_desc *d) {
     uint32_t *sph_body = reinterpret_cast<uint32_t *>(hs + off_sphb), *misc_body = reinterpret_cast<uint32_t *>(hs + off_misc);
     double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};   // bounding box of the finite sphere centres
     bool have = false;
-    for (uint32_t i = 0, si = 0, mi = 0; i < n; ++i) {
-        BodyMat &m = mats[i];
-        std::memset(&m, 0, sizeof(m));
-        for (int k = 0; k < 3; ++k) m.color[k] = d->color[3 * (size_t)i + k];
+    uint32_t ns = 0, nm = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        BodyMat m;
+        m.color[0] = d->color[3 * (size_t)i]; m.color[1] = d->color[3 * (size_t)i + 1]; m.color[2] = d->color[3 * (size_t)i + 2];
         m.albedo = d->albedo[i];
         m.p0 = d->surface_param[2 * (size_t)i];
         m.p1 = d->surface_param[2 * (size_t)i + 1];
@@ -358,21 +352,31 @@ static int build_scene(rg_scene *sc, const rg_scene_desc *d) {
         m.tex = d->coloration_kind[i] == RG_COLORATION_TEXTURE ? d->texture_id[i] : -1;
         m.coloration = d->coloration_kind[i];
         m.surface = d->surface_kind[i];
+        m.pad[0] = m.pad[1] = 0;
+        m.pad2[0] = m.pad2[1] = 0;
+        mats[i] = m;
         const double *g = d->body_geom + 8 * (size_t)i;
         if (d->body_kind[i] == RG_BODY_SPHERE) {
-            std::memcpy(sph + 4 * (size_t)si, g, 32);
-            sph_body[si++] = i;
+            std::memcpy(sph + 4 * (size_t)ns, g, 32);
+            sph_body[ns++] = i;
             if (std::isfinite(g[0]) && std::isfinite(g[1]) && std::isfinite(g[2])) {
-                for (int k = 0; k < 3; ++k) {
-                    if (!have) { lo[k] = hi[k] = g[k]; }
-                    else { lo[k] = std::fmin(lo[k], g[k]); hi[k] = std::fmax(hi[k], g[k]); }
+                if (!have) {
+                    for (int k = 0; k < 3; ++k) lo[k] = hi[k] = g[k];
+                    have = true;
+                } else {   // plain comparisons: the operands are finite (fmin / fmax are library calls here)
+                    for (int k = 0; k < 3; ++k) {
+                        if (g[k] < lo[k]) lo[k] = g[k];
+                        if (g[k] > hi[k]) hi[k] = g[k];
+                    }
                 }
-                have = true;
             }
         } else {
-            misc_body[mi++] = i;
+            misc_body[nm++] = i;
         }
     }
+    ds.n_spheres = ns;
+    ds.n_misc = nm;
+    const size_t cull_padded = ((size_t)ns + 3) / 4 * 4;
     // P = centre of the bounding box of the sphere centres: reference point of the FP32 cull coordinates
     for (int k = 0; k < 3; ++k) ds.cull_ref[k] = have ? 0.5 * (lo[k] + hi[k]) : 0.0;
 

@@ -220,38 +220,67 @@ __global__ void __launch_bounds__(256) k_gb_count(const GridBuildParams p, const
             for (int x = a[0]; x <= b[0]; ++x) atomicAdd(&count[((size_t)z * p.dim[1] + y) * p.dim[0] + x], 1u);
 }
 
-// exclusive prefix sum of count[0, n) in place, count[n] = total; one 1024-thread block
+// exclusive prefix sum of count[0, n) in place, count[n] = total; one 1024-thread block walking the array in
+// tiles of 4096 (one coalesced 128-bit load per thread, warp shuffles, 32 warp sums through shared memory)
 __global__ void __launch_bounds__(1024) k_gb_scan(uint32_t *count, uint32_t n, uint32_t *ctr) {
-    __shared__ uint32_t part[1024];
-    const uint32_t t = threadIdx.x;
-    const uint32_t per = (n + 1023u) / 1024u;
-    const uint32_t lo = min(n, t * per), hi = min(n, lo + per);
-    uint32_t sum = 0;
-    for (uint32_t i = lo; i < hi; ++i) sum += count[i];
-    part[t] = sum;
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry;
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    if (t == 0) carry = 0;
     __syncthreads();
-    for (uint32_t off = 1; off < 1024u; off <<= 1) {   // Hillis-Steele inclusive scan of the partials
-        const uint32_t v = t >= off ? part[t - off] : 0u;
+    for (uint32_t base = 0; base < n; base += 4096u) {
+        const uint32_t i = base + 4u * t;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (i + 3u < n) v = *reinterpret_cast<const uint4 *>(count + i);
+        else {
+            if (i < n) v.x = count[i];
+            if (i + 1u < n) v.y = count[i + 1];
+            if (i + 2u < n) v.z = count[i + 2];
+        }
+        const uint32_t mine = v.x + v.y + v.z + v.w;
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += up;
+        }
+        if (lane == 31u) warp_sum[warp] = incl;
         __syncthreads();
-        part[t] += v;
+        if (warp == 0) {
+            uint32_t w = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, w, o);
+                if ((int)lane >= o) w += up;
+            }
+            warp_sum[lane] = w;   // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t before = carry + (warp ? warp_sum[warp - 1] : 0u) + (incl - mine);
+        const uint4 o4 = make_uint4(before, before + v.x, before + v.x + v.y, before + v.x + v.y + v.z);
+        if (i + 3u < n) *reinterpret_cast<uint4 *>(count + i) = o4;
+        else {
+            if (i < n) count[i] = o4.x;
+            if (i + 1u < n) count[i + 1] = o4.y;
+            if (i + 2u < n) count[i + 2] = o4.z;
+        }
+        __syncthreads();
+        if (t == 1023u) carry += warp_sum[31];
         __syncthreads();
     }
-    uint32_t run = t ? part[t - 1] : 0u;
-    for (uint32_t i = lo; i < hi; ++i) {
-        const uint32_t c = count[i];
-        count[i] = run;
-        run += c;
-    }
-    if (t == 1023u) {
-        count[n] = part[1023];
-        ctr[GB_TOTAL] = part[1023];
+    if (t == 0) {
+        count[n] = carry;
+        ctr[GB_TOTAL] = carry;
     }
 }
 
+// (the lists are written only if they fit the capacity the host allocated before it knew their size:
+// k_gb_* run back to back with no read-back in between; the host checks the total afterwards)
 __global__ void __launch_bounds__(256) k_gb_fill(const GridBuildParams p, const double4 *__restrict__ sph,
-                                                 const uint32_t *__restrict__ start, uint32_t *cursor, uint32_t *items) {
+                                                 const uint32_t *__restrict__ start, uint32_t *cursor, uint32_t *items,
+                                                 const uint32_t *__restrict__ ctr, uint32_t items_cap) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n) return;
+    if (i >= p.n || ctr[GB_TOTAL] > items_cap) return;
     int a[3], b[3];
     if (gb_classify(p, sph[i], a, b) != 2) return;
     for (int z = a[2]; z <= b[2]; ++z)
@@ -299,9 +328,10 @@ __host__ __device__ inline void gb_sort_u32(uint32_t *v, uint32_t n) {
 // per cell: sort its list by sphere index (the atomics above fill it in arbitrary order), copy the
 // cull records next to it and write the inline 48-byte record (see grid_build_host)
 __global__ void __launch_bounds__(256) k_gb_finish(uint32_t ncells, const uint32_t *__restrict__ start, uint32_t *items,
-                                                   const float4 *__restrict__ cull4, float4 *items_cull, float4 *recs) {
+                                                   const float4 *__restrict__ cull4, float4 *items_cull, float4 *recs,
+                                                   const uint32_t *__restrict__ ctr, uint32_t items_cap) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncells) return;
+    if (c >= ncells || ctr[GB_TOTAL] > items_cap) return;
     const uint32_t b0 = start[c], b1 = start[c + 1], n = b1 - b0;
     gb_sort_u32(items + b0, n);   // lists are short (mean < 1, rarely > 8)
     for (uint32_t i = b0; i < b1; ++i) items_cull[i] = cull4[items[i]];
@@ -318,8 +348,9 @@ __global__ void __launch_bounds__(256) k_gb_finish(uint32_t ncells, const uint32
     }
 }
 
-__global__ void k_gb_sort_loose(const uint32_t *tmp, uint32_t n, uint32_t *out) {   // n <= 256: one thread
+__global__ void k_gb_sort_loose(const uint32_t *tmp, const uint32_t *__restrict__ ctr, uint32_t *out) {   // <= 256 entries: one thread
     if (blockIdx.x || threadIdx.x) return;
+    const uint32_t n = ctr[GB_LOOSE] <= 256u ? ctr[GB_LOOSE] : 0u;
     for (uint32_t i = 0; i < n; ++i) {
         const uint32_t v = tmp[i];
         uint32_t j = i;
@@ -344,9 +375,10 @@ static int grid_build_device(rg_scene *sc, const double *sph, uint32_t n) {
                         std::fabs(c[0]) < 1e6 && std::fabs(c[1]) < 1e6 && std::fabs(c[2]) < 1e6 && r < 1e6;
         if (!ok) continue;
         ++binned;
-        for (int k = 0; k < 3; ++k) {
-            if (!have) { lo[k] = c[k] - r; hi[k] = c[k] + r; }
-            else { lo[k] = std::fmin(lo[k], c[k] - r); hi[k] = std::fmax(hi[k], c[k] + r); }
+        for (int k = 0; k < 3; ++k) {   // (finite operands: plain comparisons give what fmin / fmax give)
+            const double a = c[k] - r, b = c[k] + r;
+            if (!have || a < lo[k]) lo[k] = a;
+            if (!have || b > hi[k]) hi[k] = b;
         }
         have = true;
     }
@@ -369,34 +401,40 @@ static int grid_build_device(rg_scene *sc, const double *sph, uint32_t n) {
     }
     const size_t ncells = (size_t)p.dim[0] * p.dim[1] * p.dim[2];
 
-    uint32_t *start = static_cast<uint32_t *>(sc->arena.alloc((ncells + 1) * sizeof(uint32_t)));
-    uint32_t *cursor = static_cast<uint32_t *>(sc->arena.alloc(ncells * sizeof(uint32_t)));
-    uint32_t *ctr = static_cast<uint32_t *>(sc->arena.alloc(4 * sizeof(uint32_t)));
-    uint32_t *loose_tmp = static_cast<uint32_t *>(sc->arena.alloc(kGbLooseTmp * sizeof(uint32_t)));
-    if (!start || !cursor || !ctr || !loose_tmp) return RG_E_NOMEM;
+    // Capacity of the cell lists before their size is known: a sphere lands in ~2.7 cells at the default density;
+    // 8 per sphere (and never less than 4096) is generous, and a scene that needs more takes a second, exact pass.
+    uint32_t items_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(8ull * n, 4096), 0x7FFFFFFFull);
     cudaStream_t st = sc->stream;
-    RG_CUDA(cudaMemsetAsync(start, 0, (ncells + 1) * sizeof(uint32_t), st));
-    RG_CUDA(cudaMemsetAsync(cursor, 0, ncells * sizeof(uint32_t), st));
-    RG_CUDA(cudaMemsetAsync(ctr, 0, 4 * sizeof(uint32_t), st));
-    const unsigned sblocks = (n + 255) / 256;
-    k_gb_count<<<sblocks, 256, 0, st>>>(p, sc->ds.sph, start, ctr, loose_tmp);
-    k_gb_scan<<<1, 1024, 0, st>>>(start, (uint32_t)ncells, ctr);
     uint32_t h_ctr[4] = {0, 0, 0, 0};
-    RG_CUDA(cudaMemcpyAsync(h_ctr, ctr, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
-    RG_CUDA(cudaStreamSynchronize(st));
-    RG_CUDA(cudaGetLastError());
-    const uint32_t n_loose = h_ctr[GB_LOOSE], n_kept = h_ctr[GB_KEPT], total = h_ctr[GB_TOTAL];
+    uint32_t *start = nullptr, *cursor = nullptr, *ctr = nullptr, *loose_tmp = nullptr, *items = nullptr, *loose = nullptr;
+    float4 *items_cull = nullptr, *recs = nullptr;
+    for (int pass = 0; pass < 2; ++pass) {
+        start = static_cast<uint32_t *>(sc->arena.alloc((ncells + 1) * sizeof(uint32_t)));
+        cursor = static_cast<uint32_t *>(sc->arena.alloc(ncells * sizeof(uint32_t)));
+        ctr = static_cast<uint32_t *>(sc->arena.alloc(4 * sizeof(uint32_t)));
+        loose_tmp = static_cast<uint32_t *>(sc->arena.alloc(kGbLooseTmp * sizeof(uint32_t)));
+        items = static_cast<uint32_t *>(sc->arena.alloc((size_t)items_cap * sizeof(uint32_t)));
+        items_cull = static_cast<float4 *>(sc->arena.alloc((size_t)items_cap * sizeof(float4)));
+        loose = static_cast<uint32_t *>(sc->arena.alloc(256 * sizeof(uint32_t)));
+        recs = static_cast<float4 *>(sc->arena.alloc(grid_record_count(ncells, items_cap) * 3 * sizeof(float4)));
+        if (!start || !cursor || !ctr || !loose_tmp || !items || !items_cull || !loose || !recs) return RG_E_NOMEM;
+        RG_CUDA(cudaMemsetAsync(start, 0, (ncells + 1) * sizeof(uint32_t), st));
+        RG_CUDA(cudaMemsetAsync(cursor, 0, ncells * sizeof(uint32_t), st));
+        RG_CUDA(cudaMemsetAsync(ctr, 0, 4 * sizeof(uint32_t), st));
+        const unsigned sblocks = (n + 255) / 256;
+        k_gb_count<<<sblocks, 256, 0, st>>>(p, sc->ds.sph, start, ctr, loose_tmp);
+        k_gb_scan<<<1, 1024, 0, st>>>(start, (uint32_t)ncells, ctr);
+        k_gb_fill<<<sblocks, 256, 0, st>>>(p, sc->ds.sph, start, cursor, items, ctr, items_cap);
+        k_gb_finish<<<(unsigned)((ncells + 255) / 256), 256, 0, st>>>((uint32_t)ncells, start, items, sc->ds.cull4, items_cull, recs, ctr, items_cap);
+        k_gb_sort_loose<<<1, 32, 0, st>>>(loose_tmp, ctr, loose);
+        RG_CUDA(cudaGetLastError());
+        RG_CUDA(cudaMemcpyAsync(h_ctr, ctr, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
+        RG_CUDA(cudaStreamSynchronize(st));   // the one synchronisation of the build (and of the scene upload before it)
+        if (h_ctr[GB_TOTAL] <= items_cap) break;
+        items_cap = h_ctr[GB_TOTAL];          // rare: lists longer than the generous guess — once more, exactly sized
+    }
+    const uint32_t n_loose = h_ctr[GB_LOOSE], n_kept = h_ctr[GB_KEPT];
     if (n_loose > 256 || n_kept < 8) return RG_OK;   // not a scene a uniform grid suits
-    uint32_t *items = static_cast<uint32_t *>(sc->arena.alloc((size_t)std::max<uint32_t>(total, 1) * sizeof(uint32_t)));
-    float4 *items_cull = static_cast<float4 *>(sc->arena.alloc((size_t)std::max<uint32_t>(total, 1) * sizeof(float4)));
-    uint32_t *loose = static_cast<uint32_t *>(sc->arena.alloc((size_t)std::max<uint32_t>(n_loose, 1) * sizeof(uint32_t)));
-    float4 *recs = static_cast<float4 *>(sc->arena.alloc(grid_record_count(ncells, total) * 3 * sizeof(float4)));
-    if (!items || !items_cull || !loose || !recs) return RG_E_NOMEM;
-    k_gb_fill<<<sblocks, 256, 0, st>>>(p, sc->ds.sph, start, cursor, items);
-    k_gb_finish<<<(unsigned)((ncells + 255) / 256), 256, 0, st>>>((uint32_t)ncells, start, items, sc->ds.cull4, items_cull, recs);
-    if (n_loose) k_gb_sort_loose<<<1, 32, 0, st>>>(loose_tmp, n_loose, loose);
-    RG_CUDA(cudaGetLastError());
-    RG_CUDA(cudaStreamSynchronize(st));
 
     g.cell_rec = recs;
     g.cell_start = start;

@@ -16,6 +16,8 @@
 #include <mutex>
 #include <thread>
 
+#include <string>
+
 #include "rg_host.h"
 
 namespace rg {
@@ -299,3 +301,87 @@ int multi_render_rows(rg_scene *sc, uint32_t w, uint32_t h, uint32_t y0, uint32_
 }
 
 }  // namespace rg
+
+// ---- a barrier for the processes of one box (one per GPU) in shared memory ---------------------------------
+// The end of a sharded frame needs every rank to know that all rows have landed.  A collective on the GPUs for
+// that (an NCCL all-reduce of one word) costs 60-100 us per frame; the ranks have already synchronised their
+// own streams when they get here, so a sense-reversing counter in a shared-memory page does it in a few
+// microseconds — the "host std::atomic" option of the multi-GPU plan, across processes.
+#include <fcntl.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
+namespace {
+struct ShmBarrierPage {
+    std::atomic<uint32_t> arrived;
+    std::atomic<uint32_t> sense;
+    uint32_t parties;
+};
+struct ShmBarrier {
+    ShmBarrierPage *page = nullptr;
+    uint32_t local_sense = 0;
+    std::string name;
+    bool owner = false;
+};
+}  // namespace
+
+extern "C" {
+
+int rg_shm_barrier_open(const char *name, uint32_t parties, int32_t create, void **handle) {
+    if (!name || !handle || parties == 0) { rg::set_error("rg_shm_barrier_open: bad argument"); return RG_E_INVALID; }
+    *handle = nullptr;
+    static_assert(std::atomic<uint32_t>::is_always_lock_free, "shared-memory atomics must be address-free");
+    const int fd = shm_open(name, create ? (O_CREAT | O_RDWR | O_TRUNC) : O_RDWR, 0600);
+    if (fd < 0) { rg::set_error("shm_open(%s) failed", name); return RG_E_INVALID; }
+    if (create && ftruncate(fd, (off_t)sizeof(ShmBarrierPage)) != 0) { close(fd); rg::set_error("ftruncate failed"); return RG_E_NOMEM; }
+    void *p = mmap(nullptr, sizeof(ShmBarrierPage), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) { rg::set_error("mmap of the barrier page failed"); return RG_E_NOMEM; }
+    ShmBarrier *b = new ShmBarrier();
+    b->page = static_cast<ShmBarrierPage *>(p);
+    b->name = name;
+    b->owner = create != 0;
+    if (create) {   // (a fresh shared-memory object is zero-filled; the creator publishes its name only after this)
+        b->page->arrived.store(0);
+        b->page->sense.store(0);
+        b->page->parties = parties;
+    }
+    *handle = b;
+    return RG_OK;
+}
+
+int rg_shm_barrier_wait(void *handle) {
+    ShmBarrier *b = static_cast<ShmBarrier *>(handle);
+    if (!b || !b->page) { rg::set_error("rg_shm_barrier_wait: bad handle"); return RG_E_INVALID; }
+    ShmBarrierPage *pg = b->page;
+    const uint32_t my = b->local_sense ^ 1u;
+    b->local_sense = my;
+    if (pg->arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == pg->parties) {
+        pg->arrived.store(0, std::memory_order_relaxed);
+        pg->sense.store(my, std::memory_order_release);
+        return RG_OK;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t spins = 0; pg->sense.load(std::memory_order_acquire) != my; ++spins) {
+        if ((spins & 1023u) == 1023u) {
+            sched_yield();
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) {
+                rg::set_error("rg_shm_barrier_wait: a rank did not arrive within 120 s");
+                return RG_E_CANCELLED;
+            }
+        }
+    }
+    return RG_OK;
+}
+
+int rg_shm_barrier_close(void *handle) {
+    ShmBarrier *b = static_cast<ShmBarrier *>(handle);
+    if (!b) return RG_OK;
+    if (b->page) munmap(b->page, sizeof(ShmBarrierPage));
+    if (b->owner) shm_unlink(b->name.c_str());
+    delete b;
+    return RG_OK;
+}
+
+}  // extern "C"

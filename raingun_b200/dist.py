@@ -173,6 +173,40 @@ def _session_nonce(store, rank: int) -> str:
     return _SESSIONS[sid]
 
 
+class HostBarrier:
+    """End-of-frame barrier of the ranks of one box in shared memory (rg_shm_barrier_*): a few microseconds where a
+    collective on the GPUs takes 60-100.  Valid only after every rank's own device work is complete, which the
+    blocking render calls guarantee.  Rank 0 creates it and publishes the name through the store."""
+
+    def __init__(self, rank: int, world: int, store=None, tag: str = "0") -> None:
+        import ctypes
+        import os
+
+        from . import _native
+        self._native, self.world = _native, world
+        self._h = ctypes.c_void_p()
+        key = f"raingun/host_barrier/{tag}"
+        store = store or (default_store() if world > 1 else None)
+        if rank == 0:
+            name = f"/raingun_bar_{os.getpid()}_{tag}"
+            _native.check(_native.lib().rg_shm_barrier_open(name.encode(), world, 1, ctypes.byref(self._h)))
+            if world > 1:
+                store.set(key, name)
+        else:
+            name = bytes(store.get(key)).decode()
+            _native.check(_native.lib().rg_shm_barrier_open(name.encode(), world, 0, ctypes.byref(self._h)))
+
+    def wait(self) -> None:
+        self._native.check(self._native.lib().rg_shm_barrier_wait(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            if self.world > 1:
+                dist.barrier()   # nobody is still waiting on the page
+            self._native.lib().rg_shm_barrier_close(self._h)
+            self._h = None
+
+
 class SharedHostFrame:
     """One frame in HOST memory that every rank of the box writes its rows into: a shared-memory file mapped
     and pinned (``rg_host_register``) in each process, so every GPU delivers its rows over its own PCIe link
@@ -304,7 +338,8 @@ def render_frame_sharded(render_rowlist: Union[Callable[[np.ndarray, torch.Tenso
                          tile_rows: int = DEFAULT_TILE_ROWS, schedule: str = "auto",
                          gather: bool = True, staging: Optional[torch.Tensor] = None,
                          gather_mode: str = "reduce", frame_buf: Optional[torch.Tensor] = None,
-                         lead: float = 0.6, peer_frames: Optional[PeerFrames] = None) -> ShardResult:
+                         lead: float = 0.6, peer_frames: Optional[PeerFrames] = None,
+                         host_barrier: Optional["HostBarrier"] = None) -> ShardResult:
     """Renders one frame across ``world`` ranks.
 
     ``render_rowlist(rows, out)`` must fill ``out`` (a uint8 tensor of ``len(rows)*width*4``
@@ -416,7 +451,10 @@ def render_frame_sharded(render_rowlist: Union[Callable[[np.ndarray, torch.Tenso
 
     if peer:   # the rows are already in rank 0's frame (GPU memory, or pinned host memory); make that known
         if world > 1:
-            dist.barrier()
+            if host_barrier is not None:   # every rank's render call has synchronised its own stream: a CPU barrier is enough
+                host_barrier.wait()
+            else:
+                dist.barrier()
         check_all_rows_rendered()
         if host:
             res.frame = torch.from_numpy(peer_frames.array(frame_id)) if rank == 0 else None

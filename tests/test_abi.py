@@ -102,7 +102,7 @@ def test_headers_are_plain_c(tmp_path):
         "    /* take the address of every entry point a host would bind */\n"
         "    void *fns[] = {(void *)rg_scene_create, (void *)rg_scene_create_multi, (void *)rg_scene_device_count, (void *)rg_scene_destroy, (void *)rg_scene_set_option, (void *)rg_render,\n"
         "                   (void *)rg_render_rows, (void *)rg_render_rows_device, (void *)rg_render_rowlist_device,\n"
-        "                   (void *)rg_render_rowlist_scatter, (void *)rg_render_rowlist_host, (void *)rg_host_register, (void *)rg_host_unregister, (void *)rg_device_enable_peer, (void *)rg_shared_frame_create, (void *)rg_shared_frame_open,\n"
+        "                   (void *)rg_render_rowlist_scatter, (void *)rg_render_rowlist_host, (void *)rg_host_register, (void *)rg_host_unregister, (void *)rg_device_enable_peer, (void *)rg_shm_barrier_open, (void *)rg_shm_barrier_wait, (void *)rg_shm_barrier_close, (void *)rg_shared_frame_create, (void *)rg_shared_frame_open,\n"
         "                   (void *)rg_shared_frame_close, (void *)rg_render_stream, (void *)rg_render_rows_f32, (void *)rg_render_stream_f32, (void *)rg_trim, (void *)rg_last_error, (void *)rg_device_count,\n"
         "                   (void *)rgh_scene_load, (void *)rgh_scene_parse, (void *)rgh_scene_desc, (void *)rgh_scene_destroy,\n"
         "                   (void *)rgh_jpeg_decode, (void *)rgh_png_decode, (void *)rgh_png_encode, (void *)rgh_image_open,\n"

@@ -38,12 +38,13 @@ def _worker(rank, world, port, schedule, out_dir, gather_mode="p2p", workers=1):
         calls.append(len(rows))
         return len(rows)
 
-    host_frames = None
+    host_frames = host_barrier = None
     if gather_mode == "host":   # one shared host frame every rank writes its rows into (pinning needs CUDA: off here)
         import ctypes
 
-        from raingun_b200.dist import SharedHostFrame
+        from raingun_b200.dist import HostBarrier, SharedHostFrame
         host_frames = SharedHostFrame(W, H, rank, world, pin=False)
+        host_barrier = HostBarrier(rank, world)   # the shared-memory end-of-frame barrier instead of a collective
 
         def render_rowlist(rows, frame_ptr):   # noqa: F811 - the "host" flavour: row y goes to frame_ptr + y * W * 4
             frame = np.ctypeslib.as_array(ctypes.cast(frame_ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(H, W, 4))
@@ -58,7 +59,8 @@ def _worker(rank, world, port, schedule, out_dir, gather_mode="p2p", workers=1):
     for it, frame_id in enumerate((1, 2, 1, 1)):
         res = render_frame_sharded(render_rowlist if workers == 1 else [render_rowlist] * workers, W, H, rank, world,
                                    frame_id, torch.device("cpu"),
-                                   tile_rows=TILE, schedule=schedule, gather_mode=gather_mode, peer_frames=host_frames)
+                                   tile_rows=TILE, schedule=schedule, gather_mode=gather_mode, peer_frames=host_frames,
+                                   host_barrier=host_barrier)
         tiles.append(sorted(res.my_tiles))
         if rank == 0:
             np.save(os.path.join(out_dir, f"frame{it}.npy"), np.array(res.frame.numpy()))
@@ -68,6 +70,7 @@ def _worker(rank, world, port, schedule, out_dir, gather_mode="p2p", workers=1):
             dist.barrier()
     if host_frames is not None:
         host_frames.close()
+        host_barrier.close()
     np.save(os.path.join(out_dir, f"tiles{rank}.npy"), np.array(tiles[0], dtype=np.int64))
     dist.barrier()
     dist.destroy_process_group()
