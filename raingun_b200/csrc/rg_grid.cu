@@ -11,10 +11,13 @@
 
 namespace rg {
 
-// cells per sphere; measured on the B200 (C4 / C5 ms per frame): 2 -> 26.20 / 266.9, 3 -> 25.71 / 263.9, 4 -> 25.96 / 268.3,
-// 6 -> 26.67 / 282.0, 8 -> 27.35 / 301.3 (RG_GRID_DENSITY overrides, for tuning runs)
+// cells per sphere (RG_GRID_DENSITY overrides, for tuning runs).  Measured on the B200, C4 / C5 ms per frame.  Round 1's
+// kernel: 2 -> 26.20 / 266.9, 3 -> 25.71 / 263.9, 4 -> 25.96 / 268.3, 6 -> 26.67 / 282.0.  Round 2's (chained records: a
+// crowded cell costs one more record, exactly what a cell visit costs, so fewer, fuller cells win): 0.5 -> 19.76 / 200.2,
+// 0.75 -> 19.02 / 187.9, 1 -> 18.90 / 183.5, 1.25 -> 18.77 / 184.1, 1.5 -> 18.86 / 185.6, 2 -> 19.21 / 189.7, 3 -> 19.84 / 200.4,
+// 4 -> 20.58 / 209.7, 6 -> 21.71 / 227.6.
 static double grid_density() {
-    static const double d = [] { const char *e = getenv("RG_GRID_DENSITY"); double v = e ? atof(e) : 0.0; return v > 0.0 ? v : 3.0; }();
+    static const double d = [] { const char *e = getenv("RG_GRID_DENSITY"); double v = e ? atof(e) : 0.0; return v > 0.0 ? v : 1.25; }();
     return d;
 }
 
