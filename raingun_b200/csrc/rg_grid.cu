@@ -135,7 +135,8 @@ static int grid_build_host(rg_scene *sc, const double *sph, uint32_t n) {
     // lane.  Record c is cell c's first; a cell with more than two items (a few per cent at the default
     // density) continues in chained records behind the cells' own (grid_chain_record), which the tracer reads
     // exactly like a first record: one instruction stream for every scanning lane, no separate overflow
-    // path.  Empty slots hold a record that every cullable ray rejects.
+    // path.  Empty slots hold a record that every cullable ray rejects.  (Three items per 64-byte record — fewer
+    // chained records, one more cull per visit — was measured: C4 18.8 -> 19.5 ms, C5 186 -> 198 ms at its own best density.)
     const float kInf = std::numeric_limits<float>::infinity();
     const size_t nrecs = grid_record_count(ncells, start[ncells]);
     std::vector<float4> recs(nrecs * 3, make_float4(0.f, 0.f, 0.f, kInf));
