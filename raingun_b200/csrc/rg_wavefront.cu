@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(256, RG_SHADE_MINB) k_shade(const DScene s, co
         // hit_point + n * SHADOW_BIAS towards the light; the light-dependent scalars are kept
         // for k_diffuse.  (Doing this warp-cooperatively — one (hit, light) pair per lane instead of a
         // per-light loop in the ~third of the lanes that are lit — was measured: no gain once the kernel
-        // runs at 64 registers; it waits on gathers, not on issue slots.)
+        // runs at 64 registers; it waits on gathers, not on issue slots.  Likewise partitioning a block's rays
+        // into misses / refractive hits / lit hits so that every warp runs one path: 18.83 vs 18.93 ms.)
         const uint32_t j = base_lit + __popc(m_lit & lt);
         lb.lit_node[j] = i;
         lb.lit_bc[j] = make_float4(bc.r, bc.g, bc.b, s.mat[body].albedo);
