@@ -19,3 +19,13 @@ except Exception as e:
     print("N=$n ERR", e); print(open("gpurun_out/scale_$n.err").read()[-1500:])
 PY
 done
+# optional extra: tile heights at the largest N (bash tests/_scale.sh "8" "4 16")
+for tr in ${2:-}; do
+  n=$(echo $1 | awk '{print $NF}')
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29700+tr)) bench.py --gpus $n --steps 8 --warmup 3 --no-cpu-baseline --no-roofline --no-configs --no-in-library --tile-rows $tr > gpurun_out/scale_${n}_t$tr.json 2> gpurun_out/scale_${n}_t$tr.err
+  python - <<PY
+import json
+d=json.loads(open("gpurun_out/scale_${n}_t$tr.json").read().strip().splitlines()[-1])
+print("N=$n tile-rows $tr: value %.1f Mrays/s %.2f ms | e2e %.2f ms" % (d["value"], d["ms_per_step"], d["e2e"]["ms_per_step"]))
+PY
+done
