@@ -321,7 +321,8 @@ static int build_scene(rg_scene *sc, const rg_scene_desc *d) {
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t off_kind = 0, off_geom = align(off_kind + n), off_mat = align(off_geom + (size_t)n * 64),
                  off_sph = align(off_mat + (size_t)n * sizeof(BodyMat)), off_sphb = align(off_sph + (size_t)n * 32),
-                 off_misc = align(off_sphb + (size_t)n * 4), total = align(off_misc + (size_t)n * 4);
+                 off_misc = align(off_sphb + (size_t)n * 4), off_bsph = align(off_misc + (size_t)n * 4),
+                 total = align(off_bsph + (size_t)n * 4);
     if (sc->h_stage_cap < total) {
         if (sc->h_stage) cudaFreeHost(sc->h_stage);
         sc->h_stage = nullptr;
@@ -338,6 +339,7 @@ static int build_scene(rg_scene *sc, const rg_scene_desc *d) {
     BodyMat *mats = reinterpret_cast<BodyMat *>(hs + off_mat);
     double *sph = reinterpret_cast<double *>(hs + off_sph);
     uint32_t *sph_body = reinterpret_cast<uint32_t *>(hs + off_sphb), *misc_body = reinterpret_cast<uint32_t *>(hs + off_misc);
+    uint32_t *body_sph = reinterpret_cast<uint32_t *>(hs + off_bsph);
     double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};   // bounding box of the finite sphere centres
     bool have = false;
     uint32_t ns = 0, nm = 0;
@@ -358,6 +360,7 @@ static int build_scene(rg_scene *sc, const rg_scene_desc *d) {
         const double *g = d->body_geom + 8 * (size_t)i;
         if (d->body_kind[i] == RG_BODY_SPHERE) {
             std::memcpy(sph + 4 * (size_t)ns, g, 32);
+            body_sph[i] = ns;
             sph_body[ns++] = i;
             if (std::isfinite(g[0]) && std::isfinite(g[1]) && std::isfinite(g[2])) {
                 if (!have) {
@@ -371,6 +374,7 @@ static int build_scene(rg_scene *sc, const rg_scene_desc *d) {
                 }
             }
         } else {
+            body_sph[i] = 0xFFFFFFFFu;
             misc_body[nm++] = i;
         }
     }
@@ -408,6 +412,7 @@ static int build_scene(rg_scene *sc, const rg_scene_desc *d) {
     ds.sph = ns ? reinterpret_cast<const double4 *>(dev + off_sph) : nullptr;
     ds.sph_body = ns ? reinterpret_cast<const uint32_t *>(dev + off_sphb) : nullptr;
     ds.misc_body = nm ? reinterpret_cast<const uint32_t *>(dev + off_misc) : nullptr;
+    ds.body_sph = n ? reinterpret_cast<const uint32_t *>(dev + off_bsph) : nullptr;
     ds.cull4 = ns ? cull4 : nullptr;
     ds.cull2 = ns ? cull2 : nullptr;
     if (cull_padded) {

@@ -59,6 +59,10 @@ constexpr float kFltBig = 3.4e38f;
 __host__ __device__ inline uint32_t grid_chain_record(uint32_t ncells, uint32_t pos) { return ncells + (pos >> 1); }
 __host__ __device__ inline size_t grid_record_count(size_t ncells, size_t total_items) { return ncells + total_items / 2 + 1; }
 
+#ifdef RG_GRID_DEBUG
+static __device__ unsigned long long rg_grid_dbg[2][16];
+#endif
+
 template <bool ANY>
 struct GridHit {
     Nearest best;
@@ -98,6 +102,14 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
     const uint32_t seg_len = segment_length(a);
     unsigned n_exact = 0, nan_count = 0;
     unsigned long long st_cells = 0, st_fetch = 0, st_culls = 0, st_refills = 0, st_lane_steps = 0, st_lane_slots = 0;
+#ifdef RG_GRID_DEBUG
+    unsigned long long dbg[16] = {0};
+    uint32_t last_sph = kNoSphere, last_sph2 = kNoSphere;
+    long long tmark = clock64();
+#define DBG_PHASE(k) if (STATS) { long long now_ = clock64(); dbg[k] += (unsigned long long)(now_ - tmark); tmark = now_; }
+#else
+#define DBG_PHASE(k)
+#endif
 
     // ---- per-lane ray state
     bool active = false;        // this lane owns an unfinished ray
@@ -118,6 +130,8 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
     int cell = 0, scx = 0, scy = 0, scz = 0;                   // linear index of the next cell to examine, per-axis stride (signed)
     uint32_t pend0 = kNoSphere, pend1 = kNoSphere;             // cull survivors waiting for their exact test
     uint32_t chain = 0;                                        // next record of the cell being examined (0: none, enter the next cell)
+    uint32_t skip = kNoSphere;                                 // a sphere whose exact result for this ray is already known: the origin hint
+                                                               // (rg_trace.cuh), then the sphere tested last (it is listed in the next cells too)
     bool exhausted = false;                                    // warp-uniform: the queue has no more rays
     h.best.init();
     h.occluded = false;
@@ -145,6 +159,10 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
             base = __shfl_sync(0xffffffffu, base, 0);
             exhausted = base + (uint32_t)__popc(idle) >= n_rays;
             if (STATS && lane == 0) ++st_refills;
+#ifdef RG_GRID_DEBUG
+            if (STATS && lane == 0) dbg[12] += __popc(idle);
+            last_sph = last_sph2 = (!active) ? kNoSphere : last_sph;
+#endif
             const uint32_t ri = base + __popc(idle & lanemask_lt);
             if (!active && ri < n_rays) {
                 // ---- set a new ray up: non-sphere bodies, loose spheres, clip to the grid
@@ -154,6 +172,7 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
                 chain = 0;
                 pi = phys_index(seg_len, a.seg_stride, ri);
                 const Ray ray = load_ray(a.q, pi);
+                skip = a.q.hint[pi];
                 h.best.init();
                 h.occluded = false;
                 h.tmax = ANY ? a.tmax[pi] : 0.0;
@@ -166,6 +185,8 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
                     }
                 }
                 n_exact += s.n_misc;
+                if (ANY && skip == kHintOccluded) h.occluded = true;   // the sphere the ray starts on is in the way
+                if (!(ANY && h.occluded)) {
                 cr = make_cull_ray(s, ray, true);
                 D3 op = ray.o - d3(s.cull_ref[0], s.cull_ref[1], s.cull_ref[2]);
                 const double D2 = dot(ray.d, ray.d);
@@ -212,15 +233,15 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
                             dgz = (float)ray.d.z * g.inv_cell[2];
                 const bool walkable = fabs(D2 - 1.0) <= kGridUnitTol && (misses_box || (fabsf(ogx) <= kGridMaxCoord &&
                                       fabsf(ogy) <= kGridMaxCoord && fabsf(ogz) <= kGridMaxCoord));   // false on NaN
-                if (!(ANY && h.occluded)) {
+                {
                     if (!walkable) {
                         // outside the conservativeness argument: scan every sphere (cull + exact)
                         for (uint32_t q = 0; q < s.n_spheres; ++q)
-                            if (!cull_reject(cr, s.cull4[q])) exact_sphere<ANY>(s, ray, q, h, n_exact, nan_count);
+                            if (q != skip && !cull_reject(cr, s.cull4[q])) exact_sphere<ANY>(s, ray, q, h, n_exact, nan_count);
                     } else {
                         for (uint32_t q = 0; q < g.n_loose; ++q) {
                             const uint32_t sp = g.loose[q];
-                            if (!cull_reject(cr, s.cull4[sp])) exact_sphere<ANY>(s, ray, sp, h, n_exact, nan_count);
+                            if (sp != skip && !cull_reject(cr, s.cull4[sp])) exact_sphere<ANY>(s, ray, sp, h, n_exact, nan_count);
                         }
                         // clip the ray to the grid box [0, dim]
                         const float ix = 1.0f / dgx, iy = 1.0f / dgy, iz = 1.0f / dgz;
@@ -264,9 +285,11 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
                         }
                     }
                 }
+                }   // not occluded by a body tested above / by the origin hint
             }
         }
 
+        DBG_PHASE(0)
         // ================= (B) scan: one 48-byte record per step ======================================
         // A scanning lane fetches ONE record per step and culls its two items: either the first record of
         // the next cell of its walk — the DDA then advances to the cell after it WHILE the fetch is in flight
@@ -308,18 +331,45 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
                     tcur = fmaxf(kx, fmaxf(ky, kz)) > 0.0f ? kFltInf : tnext;
                 }
                 if (STATS) { st_cells += enter ? 1u : 0u; st_fetch += (cm.x != kNoSphere) ? 1u : 0u; st_culls += (cm.x != kNoSphere) + (cm.y != kNoSphere); }
-                if (cm.x != kNoSphere && !cull_reject(cr, c0)) pend0 = cm.x;
-                if (cm.y != kNoSphere && !cull_reject(cr, c1)) pend1 = cm.y;
+                // (an empty slot holds kNoSphere: "parking" it parks nothing, so it needs no test of its own)
+                if (cm.x != skip && !cull_reject(cr, c0)) pend0 = cm.x;
+                if (cm.y != skip && !cull_reject(cr, c1)) pend1 = cm.y;
                 chain = cm.z;
             }
         }
 
+        DBG_PHASE(1)
         // ================= (C) exact tests of the parked candidates, many lanes at a time ==========
         const bool has_pending = pend0 != kNoSphere || pend1 != kNoSphere;
         const uint32_t waiting = __ballot_sync(0xffffffffu, has_pending);
         const uint32_t scanning = __ballot_sync(0xffffffffu, active && walking && !has_pending);
         if (waiting && (__popc(waiting) >= a.g_quorum || scanning == 0u ||
                         (exhausted && __popc(waiting) * 2 >= __popc(waiting | scanning)))) {
+#ifdef RG_GRID_DEBUG
+            if (STATS) {
+                if (lane == 0) { dbg[3] += 1; dbg[4] += __popc(waiting); }
+                if (RG_GRID_DEBUG >= 2 && has_pending) {
+                    const Ray ray = load_ray(a.q, pi);
+                    for (int w = 0; w < 2; ++w) {
+                        const uint32_t sp_i = w ? pend1 : pend0;
+                        if (sp_i == kNoSphere) continue;
+                        dbg[5] += 1;
+                        if (sp_i == last_sph || sp_i == last_sph2) dbg[10] += 1;
+                        last_sph2 = last_sph; last_sph = sp_i;
+                        const double4 sp = s.sph[sp_i];
+                        D3 hyp = d3(sp.x, sp.y, sp.z) - ray.o;
+                        double adj = dot(hyp, ray.d);
+                        double opp2 = dot(hyp, hyp) - (adj * adj);
+                        double r2 = sp.w * sp.w;
+                        double t;
+                        if (opp2 > r2) dbg[6] += 1;
+                        else if (!sphere_intersect(sp.x, sp.y, sp.z, sp.w, ray, t)) { dbg[7] += 1; if (fabs(dot(hyp, hyp) - r2) < 1e-6 * r2) dbg[11] += 1; }
+                        else if (ANY ? !(t <= h.tmax) : !(t < h.best.t || !h.best.found())) dbg[8] += 1;
+                        else dbg[9] += 1;
+                    }
+                }
+            }
+#endif
             if (has_pending) {
                 // every waiting lane runs the first test together; a second survivor of the same record is rare
                 const Ray ray = load_ray(a.q, pi);
@@ -327,11 +377,26 @@ __global__ void __launch_bounds__(kGridTraceThreads, RG_GRID_MINB) k_trace_grid(
                 const uint32_t second = pend0 != kNoSphere ? pend1 : kNoSphere;
                 exact_sphere<ANY>(s, ray, first, h, n_exact, nan_count);
                 if (second != kNoSphere) exact_sphere<ANY>(s, ray, second, h, n_exact, nan_count);
+                skip = second != kNoSphere ? second : first;   // re-listed in the cells that follow: same ray, same answer
                 pend0 = pend1 = kNoSphere;
                 boundf = h.bound() - t0f;
             }
         }
+        DBG_PHASE(2)
+#ifdef RG_GRID_DEBUG
+        if (STATS && lane == 0) dbg[13] += 1;
+#endif
     }
+#ifdef RG_GRID_DEBUG
+    if (STATS) {
+        for (int k = 0; k < 16; ++k) {
+            unsigned long long v = dbg[k];
+            const bool lane0_only = k <= 4 || k == 13 || k == 12;
+            if (!lane0_only) for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && v) atomicAdd(&rg_grid_dbg[ANY ? 1 : 0][k], v);
+        }
+    }
+#endif
 
     unsigned long long ne = n_exact;
 #pragma unroll

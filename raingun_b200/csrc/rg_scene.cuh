@@ -70,6 +70,7 @@ struct DScene {
     const BodyMat *mat;
     const double4 *sph;           // [n_spheres] cx, cy, cz, r
     const uint32_t *sph_body;     // [n_spheres] original body index
+    const uint32_t *body_sph;     // [n_bodies] the body's index in the sphere list (0xFFFFFFFF: not a sphere)
     const float4 *cull4;          // [n_spheres] c - P (f32), K - m_s       (rg_trace.cuh)
     const float4 *cull2;          // the same records pair-interleaved for FFMA2: (x0,x1,y0,y1)(z0,z1,-K0,-K1)
     const uint32_t *misc_body;    // [n_misc] original body index

@@ -30,7 +30,23 @@ constexpr int kSlotBits = 10;                       // local ray slot: r * 256 +
 
 struct RayQueue {            // 3 x double2 per ray: (ox,oy) (oz,dx) (dy,dz) — 128-bit coalesced traffic
     double2 *a, *b, *c;
+    uint32_t *hint;          // per ray, from the kernel that made it (k_shade): see kHintOccluded / origin_hint
 };
+constexpr size_t kRayBytes = 48 + 4;     // bytes of queue storage per ray
+
+// Origin hints.  A secondary ray starts on the body it leaves, 1e-13 outside (or inside) its surface: far too
+// close for the FP32 cull to tell, so the grid tracer used to spend one exact FP64 test per ray on that sphere
+// just to learn "behind the origin" (a third of all its exact tests, measured).  k_shade knows the body, runs the
+// reference's test (sphere_intersect, the same function on the same FP64 ray the tracer would load) once, at
+// full lane occupancy, and leaves the outcome with the ray:
+//   a sphere-list index   that sphere returns None (or, for a shadow ray, a hit beyond the light) for this ray:
+//                         the tracer may skip it — Scene::trace is a minimum, a None contributes nothing;
+//   kHintOccluded         (shadow rays) the ray's own sphere is hit before the light: shade_diffuse's answer is
+//                         "not in light" whatever else the ray meets (rendering.rs:150-155);
+//   0xFFFFFFFF            nothing known.
+// Trace kernels are free to ignore hints (the brute-force ones do): the result is the same.
+constexpr uint32_t kHintNone = 0xFFFFFFFFu;
+constexpr uint32_t kHintOccluded = 0xFFFFFFFEu;
 
 struct TraceArgs {
     RayQueue q;

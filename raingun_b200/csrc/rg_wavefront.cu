@@ -22,6 +22,14 @@
 #include "rg_host.h"
 #include "rg_trace.cuh"
 
+#ifdef RG_GRID_DEBUG
+extern "C" int rg_debug_grid_counters(unsigned long long *out, int reset) {
+    if (out && cudaMemcpyFromSymbol(out, rg::rg_grid_dbg, sizeof(unsigned long long) * 32) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[32] = {0}; if (cudaMemcpyToSymbol(rg::rg_grid_dbg, z, sizeof z) != cudaSuccess) return -1; }
+    return 0;
+}
+#endif
+
 namespace rg {
 
 constexpr uint32_t kChildDefault = 0xFFFFFFFFu;   // child colour is scene.default_color (no node)
@@ -48,6 +56,7 @@ struct LevelBuffers {
     uint32_t level;                  // recursion depth of this level
     uint32_t count_on_device;        // shadow rays / deepest level are counted in DCounters (host-free loop)
     uint32_t last_enqueued;          // no launch follows for this level's children (depth hint): flag them
+    uint32_t hints;                  // the tracer reads origin hints (rg_trace.cuh): compute them; else leave kHintNone
 };
 
 // Size of a level as its kernels see it (host-sized, or read from the device and clamped to the capacity).
@@ -92,6 +101,22 @@ __global__ void __launch_bounds__(256) k_generate(const DScene s, RayQueue q, ui
     const uint32_t k = y0 + r;
     const uint32_t y = rows ? rows[k] : k;
     store_ray(q, i, create_prime(s, x, y, width, height));
+    q.hint[i] = kHintNone;   // camera rays start on no body
+}
+
+// Origin hints of the rays k_shade makes (rg_trace.cuh): `og` = geom of the sphere the ray starts on (nullptr: none,
+// or hints are off), `own` = its sphere-list index.
+__device__ __forceinline__ uint32_t path_origin_hint(const double *og, uint32_t own, const Ray &r) {
+    if (!og) return kHintNone;
+    double t;
+    return sphere_intersect(og[0], og[1], og[2], og[3], r, t) ? kHintNone : own;   // a hit: the tracer finds it itself
+}
+__device__ __forceinline__ uint32_t shadow_origin_hint(const double *og, uint32_t own, const Ray &r, double tmax) {
+    if (!og) return kHintNone;
+    double t;
+    if (!sphere_intersect(og[0], og[1], og[2], og[3], r, t)) return own;
+    if (t <= tmax) return kHintOccluded;   // rendering.rs:150-155: nearest.distance <= light distance for some body
+    return t == t ? own : kHintNone;       // beyond the light: contributes nothing; NaN: the tracer counts it (scene.rs:38)
 }
 
 #ifndef RG_SHADE_MINB
@@ -187,13 +212,23 @@ __global__ void __launch_bounds__(256, RG_SHADE_MINB) k_shade(const DScene s, co
     const uint32_t base_lit = sh_base[0] + __shfl_sync(0xffffffffu, w_lit, 0);
     const uint32_t base_next = sh_base[1] + __shfl_sync(0xffffffffu, w_next, 0);
     uint32_t child_refl = kChildDefault, child_trans = kChildDefault;
+    // origin hints (rg_trace.cuh): every ray made here starts on `body`; if that is a sphere, run the reference's
+    // test of this very ray against it now (geom[body] holds the same four doubles as the sphere list)
+    const double *og = nullptr;
+    uint32_t own = kHintNone;
+    if (lb.hints && body != kNoBody && s.kind[body] == RG_BODY_SPHERE) {
+        own = s.body_sph[body];
+        og = s.geom + 8 * (size_t)body;
+    }
     if (want_refl) {
         child_refl = base_next + __popc(m_refl & lt);
         store_ray(lb.next, child_refl, refl);
+        lb.next.hint[child_refl] = path_origin_hint(og, own, refl);
     }
     if (want_trans) {
         child_trans = base_next + __popc(m_refl) + __popc(m_trans & lt);
         store_ray(lb.next, child_trans, trans);
+        lb.next.hint[child_trans] = path_origin_hint(og, own, trans);
     }
     if (want_lit) {
         // shade_diffuse's per-light setup (rendering.rs:141-149,163): shadow ray from
@@ -212,7 +247,9 @@ __global__ void __launch_bounds__(256, RG_SHADE_MINB) k_shade(const DScene s, co
             sh.d = light_direction_from(L, hp);
             const uint32_t k = l * lb.shadow_sl + j * lb.shadow_sj;
             store_ray(lb.shadow, k, sh);
-            lb.s_tmax[k] = light_distance(L, hp);
+            const double tmax = light_distance(L, hp);
+            lb.s_tmax[k] = tmax;
+            lb.shadow.hint[k] = shadow_origin_hint(og, own, sh, tmax);
             lb.s_ab[k] = make_float2(fmaxf((float)dot(n, sh.d), 0.0f), light_intensity(L, hp));
         }
     }
@@ -382,6 +419,7 @@ static RayQueue make_queue(DeviceBuffer &b, size_t cap) {
     q.a = b.as<double2>();
     q.b = q.a + cap;
     q.c = q.b + cap;
+    q.hint = reinterpret_cast<uint32_t *>(q.c + cap);
     return q;
 }
 
@@ -531,7 +569,7 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
 
     std::vector<uint32_t> level_n;
     uint32_t n = npix, d = 0;
-    if ((rc = wf.ray[0].reserve((size_t)n * 48))) return rc;
+    if ((rc = wf.ray[0].reserve((size_t)n * kRayBytes))) return rc;
     RayQueue cur = make_queue(wf.ray[0], n);
     const PixelOrder po = pixel_order(width, y1 - y0);
     k_generate<<<blocks(n), 256, 0, stream>>>(ds, cur, width, height, y0, npix, d_rows, nullptr, po);
@@ -552,9 +590,9 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
         if ((rc = wf.hit_t.reserve((size_t)n * 8))) return rc;
         if ((rc = wf.hit_body.reserve((size_t)n * 4))) return rc;
         DeviceBuffer &nextbuf = wf.ray[(d + 1) & 1];
-        if ((rc = nextbuf.reserve((size_t)std::max<uint64_t>(next_cap, 1) * 48))) return rc;
+        if ((rc = nextbuf.reserve((size_t)std::max<uint64_t>(next_cap, 1) * kRayBytes))) return rc;
         const int p = overlap ? (int)(d & 1u) : 0;   // parity of the shadow-side buffers
-        if ((rc = wf.sray[p].reserve((size_t)std::max<uint64_t>(shadow_cap, 1) * 48))) return rc;
+        if ((rc = wf.sray[p].reserve((size_t)std::max<uint64_t>(shadow_cap, 1) * kRayBytes))) return rc;
         if ((rc = wf.s_tmax[p].reserve((size_t)std::max<uint64_t>(shadow_cap, 1) * 8))) return rc;
         if ((rc = wf.s_ab[p].reserve((size_t)std::max<uint64_t>(shadow_cap, 1) * 8))) return rc;
         if ((rc = wf.s_lit[p].reserve((size_t)std::max<uint64_t>(shadow_cap, 1)))) return rc;
@@ -601,6 +639,7 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
         lb.cap_next = 0xFFFFFFFFu;   // the next queue holds 2n rays: cannot overflow
         lb.void_flag = &dc->overflow;
         lb.level = d;
+        lb.hints = use_grid ? 1u : 0u;
         RG_CUDA(cudaMemsetAsync(&dc->q_next, 0, 2 * sizeof(unsigned int), stream));
         if (shadow_done[p]) RG_CUDA(cudaStreamWaitEvent(stream, shadow_done[p], 0));   // level d-2 still reads these buffers
         k_shade<<<blocks(n), 256, 0, stream>>>(ds, lb, dc);
@@ -746,8 +785,8 @@ static int plan_batch_dev(rg_scene *sc, uint32_t npix, DevPlan &plan, bool use_g
     if ((rc = wf.hit_body.reserve((size_t)cap_all * 4))) return rc;
     for (int p = 0; p < 2; ++p) {
         const uint64_t c = std::max<uint64_t>(cap_max[p], 1), sc_ = std::max<uint64_t>(c * L, 1);
-        if ((rc = wf.ray[p].reserve((size_t)c * 48))) return rc;
-        if ((rc = wf.sray[p].reserve((size_t)sc_ * 48))) return rc;
+        if ((rc = wf.ray[p].reserve((size_t)c * kRayBytes))) return rc;
+        if ((rc = wf.sray[p].reserve((size_t)sc_ * kRayBytes))) return rc;
         if ((rc = wf.s_tmax[p].reserve((size_t)sc_ * 8))) return rc;
         if ((rc = wf.s_ab[p].reserve((size_t)sc_ * 8))) return rc;
         if ((rc = wf.s_lit[p].reserve((size_t)sc_))) return rc;
@@ -829,6 +868,7 @@ static int enqueue_batch_dev(rg_scene *sc, const DevPlan &plan, uint32_t width, 
         lb.cap_next = cap_next;
         lb.void_flag = &dc->overflow;
         lb.level = d;
+        lb.hints = use_grid ? 1u : 0u;
         lb.count_on_device = 1u;
         lb.last_enqueued = (d + 1 == plan.levels && can_spawn) ? 1u : 0u;
         if (shadow_done[p]) RG_CUDA(cudaStreamWaitEvent(stream, shadow_done[p], 0));   // level d-2 still reads these buffers
