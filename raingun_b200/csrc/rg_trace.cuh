@@ -123,6 +123,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  : "memory");
 }
 
+// max that returns NaN when either operand is NaN (SASS FMNMX.NAN); fmaxf would drop the NaN
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float d;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+__device__ __forceinline__ float4 lds128(uint32_t shared_addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(shared_addr));
+    return v;
+}
+
 // Per-ray constants of the FP32 cull (rg_cull.h), derived once from the FP64 ray.
 struct CullRay {
     float dx, dy, dz, nod;      // d, -(o'.d)
@@ -576,36 +588,91 @@ k_trace_brute_resident(const DScene s, const TraceArgs a, const uint32_t n_recor
                 }
             }
         };
-        // Hot loop: identical to the streaming kernel's, over the whole array.
-        float4 sv[U];
-        if (PF) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) sv[u] = sp[u];
-        }
-        bool prev_pass = false;
-#pragma unroll 1
-        for (uint32_t j = 0; j < cnt; j += U) {
-            float4 sc[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) sc[u] = PF ? sv[u] : sp[j + u];
-            if (PF) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) sv[u] = sp[j + U + u];   // software prefetch (kCullPad records of slack)
+        // Appends the (ray slot, sphere) pairs of the lanes with `pass` to the candidate queue.
+        auto enqueue = [&](bool pass, uint32_t sph, uint32_t slot) {
+            const uint32_t mask = __ballot_sync(0xffffffffu, pass);
+            if (mask) {
+                if (pass) cq[qn + __popc(mask & lanemask_lt)] = (sph << kSlotBits) | slot;
+                qn += __popc(mask);
+                __syncwarp();
+                if (qn >= 32u) {
+                    drain(qn - 32u, 32u);
+                    qn -= 32u;
+                    __syncwarp();
+                }
             }
-            const bool vote_prev = __any_sync(0xffffffffu, prev_pass);
-            bool any_pass = a.verify != 0;
+        };
+        // One group of U records (spheres j .. j+U-1) against my R rays: the h values (kept in registers) and whether
+        // every one of them is below its ray's threshold.  both rejected <=> max(h.x, h.y) < nthr; the NaN-propagating
+        // max keeps "NaN = test exactly".
+        auto test_group = [&](const float4 (&sc)[U], float2 (&hh)[R][U / 2]) -> bool {
+            bool all_rej = true;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
 #pragma unroll
                 for (int u = 0; u < U; u += 2) {
-                    const float2 h = cull_h2(cr[r], sc[u], sc[u + 1]);
-                    any_pass = any_pass | !(h.x < cr[r].nthr) | !(h.y < cr[r].nthr);
+                    hh[r][u / 2] = cull_h2(cr[r], sc[u], sc[u + 1]);
+                    all_rej = all_rej & (max_nan(hh[r][u / 2].x, hh[r][u / 2].y) < cr[r].nthr);
                 }
             }
-            if (vote_prev) survivors(j - U);
-            prev_pass = any_pass;
+            return !all_rej;
+        };
+        // The rare half (8 % of the groups hold a survivor): a ballot per ray and an append for each pair that passed,
+        // from the h values still in registers — not a scalar re-run of all U * R tests, which used to be ~20 % of
+        // the instructions this kernel issued.
+        auto collect = [&](const float2 (&hh)[R][U / 2], uint32_t j) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                bool pass_r = false;
+#pragma unroll
+                for (int u = 0; u < U; u += 2) pass_r = pass_r | !(hh[r][u / 2].x < cr[r].nthr) | !(hh[r][u / 2].y < cr[r].nthr);
+                if (__any_sync(0xffffffffu, pass_r)) {
+                    const uint32_t slot = r * 32 + lane;
+                    const bool live = tile_base + slot < n_rays;
+#pragma unroll
+                    for (int u = 0; u < U; u += 2) {
+                        enqueue(live && j + u < nsph && !(hh[r][u / 2].x < cr[r].nthr), j + u, slot);
+                        enqueue(live && j + u + 1 < nsph && !(hh[r][u / 2].y < cr[r].nthr), j + u + 1, slot);
+                    }
+                }
+            }
+        };
+        if (a.verify) {   // debug build of the loop: every culled pair is re-tested exactly (survivors())
+#pragma unroll 1
+            for (uint32_t j = 0; j < cnt; j += U) survivors(j);
+        } else if (PF && U == 2) {
+            // Software-pipelined by hand over two register sets: the records of the group after next are loaded
+            // before the current one is used (no register copies), and a group's vote + branch are issued after the
+            // NEXT group's FFMA2s, so that the compare -> vote -> branch latency never leaves the FMA pipe idle.
+            // cnt is a multiple of kCullPad = 4 = 2 U; the loads run up to kCullPad records past the array (slack).
+            uint32_t saddr = smem_u32(sp);
+            float4 s0[U], s1[U];
+            float2 hA[R][U / 2], hB[R][U / 2];
+            bool fB = false;
+#pragma unroll
+            for (int u = 0; u < U; ++u) s0[u] = lds128(saddr + 16u * u);
+#pragma unroll 1
+            for (uint32_t j = 0; j < cnt; j += 2 * U, saddr += 32u * U) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) s1[u] = lds128(saddr + 16u * (U + u));
+                const bool fA = test_group(s0, hA);
+                if (__any_sync(0xffffffffu, fB)) collect(hB, j - U);      // the previous turn's second group
+#pragma unroll
+                for (int u = 0; u < U; ++u) s0[u] = lds128(saddr + 16u * (2 * U + u));
+                fB = test_group(s1, hB);
+                if (__any_sync(0xffffffffu, fA)) collect(hA, j);
+            }
+            if (__any_sync(0xffffffffu, fB)) collect(hB, cnt - U);
+        } else {
+#pragma unroll 1
+            for (uint32_t j = 0; j < cnt; j += U) {
+                float4 sc[U];
+                float2 hh[R][U / 2];
+#pragma unroll
+                for (int u = 0; u < U; ++u) sc[u] = sp[j + u];
+                if (__any_sync(0xffffffffu, test_group(sc, hh))) collect(hh, j);
+            }
         }
-        if (cnt && __any_sync(0xffffffffu, prev_pass)) survivors(cnt - U);
         if (qn) drain(0u, qn);
         __syncwarp();
 

@@ -491,12 +491,17 @@ static int launch_trace(rg_scene *sc, const TraceArgs &ta, bool use_grid, cudaSt
         const unsigned blocks = (unsigned)std::min<uint64_t>((uint64_t)sc->sm_count, (tiles + (T_ / 32) - 1) / (T_ / 32));      \
         k_trace_brute_resident<ANY, R_, U_, T_, PF_><<<blocks, T_, resident_smem_bytes(n_records, R_, T_ / 32), stream>>>(sc->ds, tuned, n_records); \
     } while (0)
-        // measured on C4 (ms of trace kernels per 4K frame; streaming kernel 394.7): R=3,U=2,640 thr 356.0;
-        // R=4,U=2,512 thr 360.7; R=2,U=4,512 thr 379.5; R=2,U=4,1024 thr (64 registers, spills) 409;
-        // R=6,U=2,384 thr 408.8; R=8,U=2,256 thr 559 — register tiling pays until too few warps are left
-        switch (variant) {
+        // Measured on C4 / C3 (ms per 4K brute-force frame) with the software-pipelined loop of round 2 (rg_trace.cuh):
+        // R=4,U=2,512 thr 310.0 / 14.3;  R=3,U=2: 512 thr 313.4 / 17.6, 576 thr 322.1 / 9.1, 608 thr 322.1 / 10.1,
+        // 640 thr 326.7 / 9.8;  R=2,U=4,512 thr 353.5.  (The loop before it, R=3,U=2,640 thr: 373.5 / 9.3; the streaming
+        // kernel 394.7.)  More rays per lane amortise the record loads and the vote over more
+        // FFMA2s and win on long scans; short scans (C3: 500 groups per tile) want more warps to hide the tile prologue.
+        switch (variant ? variant : (sc->ds.n_spheres >= 4096u ? 1 : 4)) {
             case 1: RG_LAUNCH_RESIDENT(4, 2, 512, true); break;
             case 2: RG_LAUNCH_RESIDENT(2, 4, 512, true); break;
+            case 3: RG_LAUNCH_RESIDENT(3, 2, 608, true); break;
+            case 4: RG_LAUNCH_RESIDENT(3, 2, 576, true); break;
+            case 5: RG_LAUNCH_RESIDENT(3, 2, 512, true); break;
             default: RG_LAUNCH_RESIDENT(3, 2, 640, true); break;
         }
 #undef RG_LAUNCH_RESIDENT

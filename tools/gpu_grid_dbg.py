@@ -17,11 +17,16 @@ for wl in sys.argv[1:] or ["C4"]:
     sc = rg.Scene(sd)
     sc.set_option(N.OPT_TRACE_STATS, 1)
     buf = (ctypes.c_ulonglong * 32)()
-    lib.rg_debug_grid_counters(buf, 1)
+    have_dbg = hasattr(lib, "rg_debug_grid_counters")
+    if have_dbg: lib.rg_debug_grid_counters(buf, 1)
     st = sc.render_rows_device(w, h, 0, h, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    lib.rg_debug_grid_counters(buf, 1)
-    print(wl, "rays", st.rays, "ms", st.ms_device, "exact", st.exact_tests)
+    if have_dbg: lib.rg_debug_grid_counters(buf, 1)
+    print(wl, "rays", st.rays, "ms", st.ms_device, "exact", st.exact_tests, "| per ray: cells %.2f records %.2f culls %.2f; rays per refill %.1f; scan lane use %.3f" % (
+        st.grid_cells / st.rays, st.grid_fetches / st.rays, st.grid_culls / st.rays, st.rays / max(1, st.grid_refills), st.grid_lane_steps / max(1, st.grid_lane_slots)))
+    if not have_dbg:
+        sc.close()
+        continue
     for v, label in ((0, "nearest"), (1, "any-hit")):
         d = {names[k]: buf[v * 16 + k] for k in range(14)}
         cyc = d["cyc_refill"] + d["cyc_scan"] + d["cyc_exact"]
