@@ -73,9 +73,10 @@ def profiled_grid_kernel():
         text = open(path).read()
         out = {}
         for variant, label in (("0", "nearest"), ("1", "any_hit")):
-            m = re.search(r"### `void k_trace_grid<%s>.*?\n\n(.*?)\n\n" % variant, text, re.S)
-            if not m:
+            ms = list(re.finditer(r"### `void k_trace_grid<%s(?:, 0)?>.*?\n\n(.*?)\n\n" % variant, text, re.S))
+            if not ms:
                 continue
+            m = ms[-1]   # the last captured launch of the variant: a deep level (level 0 is the coherent exception)
             vals = {}
             for key, pat in (("ipc", r"IPC \(per SM, active\): ([\d.]+)"), ("issue_slots_busy_pct", r"issue slots busy %: ([\d.]+)"),
                              ("active_threads_per_warp", r"avg active threads / warp instr: ([\d.]+)"),
