@@ -144,7 +144,10 @@ enum {
                                 (rg_stats.grid_*); an instrumented kernel, slower; results unchanged */
     RG_OPT_SCHEDULE = 11,    /* multi-GPU scenes: 0 = automatic, 1 = static (tile t on device t mod N),
                                 2 = static share + a stealable tail handed out by an atomic tile counter */
-    RG_OPT_TILE_ROWS = 12    /* multi-GPU scenes: rows per tile (default 8) */
+    RG_OPT_TILE_ROWS = 12,   /* multi-GPU scenes: rows per tile (default 8) */
+    RG_OPT_ORIGIN_HINTS = 13 /* 1 (default) = every secondary ray carries the outcome of the reference's test against the
+                                sphere it starts on, and the grid tracer skips that test; 0 = off.  Results unchanged
+                                (Scene::trace is a minimum: a body proven to return None may be left out, scene.rs:34-39) */
 };
 
 /* Counters and timings of one render call.  A "ray" is one `Scene::trace`

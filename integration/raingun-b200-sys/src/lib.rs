@@ -44,6 +44,7 @@ pub const RG_OPT_GRAPH: i32 = 8;
 pub const RG_OPT_TRACE_STATS: i32 = 9;
 pub const RG_OPT_SCHEDULE: i32 = 11;
 pub const RG_OPT_TILE_ROWS: i32 = 12;
+pub const RG_OPT_ORIGIN_HINTS: i32 = 13;
 
 #[repr(C)]
 pub struct rg_texture_desc {

@@ -665,6 +665,9 @@ int rg_scene_set_option(rg_scene *sc, int32_t key, int64_t value) {
         case RG_OPT_TRACE_STATS:
             sc->trace_stats = value != 0;
             return RG_OK;
+        case RG_OPT_ORIGIN_HINTS:
+            sc->origin_hints = value != 0;
+            return RG_OK;
         default: break;
     }
     set_error("bad option key %d / value %lld", key, (long long)value);

@@ -111,6 +111,7 @@ struct rg_scene {
     int host_free = 0;                     // RG_OPT_HOST_FREE: 0 auto (on), 1 off (host-sized loop), 2 on
     int graph = 0;                         // RG_OPT_GRAPH: 0 auto, 1 off, 2 on
     bool trace_stats = false;              // RG_OPT_TRACE_STATS
+    bool origin_hints = true;              // RG_OPT_ORIGIN_HINTS
     uint32_t depth_hint = 0;               // levels the ray tree of this scene has been seen to use (0 = unknown)
     bool host_free_overflowed = false;     // a level once outgrew the default queue capacity: stay with the host-sized loop
     bool out_f32 = false;                  // this call delivers unquantised f32 colours, 3 per pixel (rg_render_rows_f32)

@@ -56,7 +56,8 @@ struct LevelBuffers {
     uint32_t level;                  // recursion depth of this level
     uint32_t count_on_device;        // shadow rays / deepest level are counted in DCounters (host-free loop)
     uint32_t last_enqueued;          // no launch follows for this level's children (depth hint): flag them
-    uint32_t hints;                  // the tracer reads origin hints (rg_trace.cuh): compute them; else leave kHintNone
+    uint32_t hints;                  // the tracer reads origin hints (rg_trace.cuh): 1 = compute them, 2 = write kHintNone
+                                     // (RG_OPT_ORIGIN_HINTS = 0), 0 = the tracer ignores them (brute force): write nothing
 };
 
 // Size of a level as its kernels see it (host-sized, or read from the device and clamped to the capacity).
@@ -216,19 +217,19 @@ __global__ void __launch_bounds__(256, RG_SHADE_MINB) k_shade(const DScene s, co
     // test of this very ray against it now (geom[body] holds the same four doubles as the sphere list)
     const double *og = nullptr;
     uint32_t own = kHintNone;
-    if (lb.hints && body != kNoBody && s.kind[body] == RG_BODY_SPHERE) {
+    if (lb.hints == 1u && body != kNoBody && s.kind[body] == RG_BODY_SPHERE) {
         own = s.body_sph[body];
         og = s.geom + 8 * (size_t)body;
     }
     if (want_refl) {
         child_refl = base_next + __popc(m_refl & lt);
         store_ray(lb.next, child_refl, refl);
-        lb.next.hint[child_refl] = path_origin_hint(og, own, refl);
+        if (lb.hints) lb.next.hint[child_refl] = path_origin_hint(og, own, refl);
     }
     if (want_trans) {
         child_trans = base_next + __popc(m_refl) + __popc(m_trans & lt);
         store_ray(lb.next, child_trans, trans);
-        lb.next.hint[child_trans] = path_origin_hint(og, own, trans);
+        if (lb.hints) lb.next.hint[child_trans] = path_origin_hint(og, own, trans);
     }
     if (want_lit) {
         // shade_diffuse's per-light setup (rendering.rs:141-149,163): shadow ray from
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(256, RG_SHADE_MINB) k_shade(const DScene s, co
             store_ray(lb.shadow, k, sh);
             const double tmax = light_distance(L, hp);
             lb.s_tmax[k] = tmax;
-            lb.shadow.hint[k] = shadow_origin_hint(og, own, sh, tmax);
+            if (lb.hints) lb.shadow.hint[k] = shadow_origin_hint(og, own, sh, tmax);
             lb.s_ab[k] = make_float2(fmaxf((float)dot(n, sh.d), 0.0f), light_intensity(L, hp));
         }
     }
@@ -644,7 +645,7 @@ static int render_batch(rg_scene *sc, uint32_t width, uint32_t height, uint32_t 
         lb.cap_next = 0xFFFFFFFFu;   // the next queue holds 2n rays: cannot overflow
         lb.void_flag = &dc->overflow;
         lb.level = d;
-        lb.hints = use_grid ? 1u : 0u;
+        lb.hints = use_grid ? (sc->origin_hints ? 1u : 2u) : 0u;
         RG_CUDA(cudaMemsetAsync(&dc->q_next, 0, 2 * sizeof(unsigned int), stream));
         if (shadow_done[p]) RG_CUDA(cudaStreamWaitEvent(stream, shadow_done[p], 0));   // level d-2 still reads these buffers
         k_shade<<<blocks(n), 256, 0, stream>>>(ds, lb, dc);
@@ -873,7 +874,7 @@ static int enqueue_batch_dev(rg_scene *sc, const DevPlan &plan, uint32_t width, 
         lb.cap_next = cap_next;
         lb.void_flag = &dc->overflow;
         lb.level = d;
-        lb.hints = use_grid ? 1u : 0u;
+        lb.hints = use_grid ? (sc->origin_hints ? 1u : 2u) : 0u;
         lb.count_on_device = 1u;
         lb.last_enqueued = (d + 1 == plan.levels && can_spawn) ? 1u : 0u;
         if (shadow_done[p]) RG_CUDA(cudaStreamWaitEvent(stream, shadow_done[p], 0));   // level d-2 still reads these buffers
@@ -943,7 +944,7 @@ static std::vector<uint64_t> graph_key(const rg_scene *sc, const DevPlan &plan, 
     const WavefrontScratch &wf = sc->wf;
     std::vector<uint64_t> k = {width, height, y0, npix, (uint64_t)(uintptr_t)d_rows, (uint64_t)(uintptr_t)d_out,
                                (uint64_t)use_grid, (uint64_t)sc->scatter_out | ((uint64_t)sc->out_f32 << 1), (uint64_t)sc->ds.max_depth, (uint64_t)sc->overlap,
-                               (uint64_t)sc->verify_cull, (uint64_t)sc->trace_stats, (uint64_t)plan.levels};
+                               (uint64_t)sc->verify_cull, (uint64_t)sc->trace_stats | ((uint64_t)sc->origin_hints << 1), (uint64_t)plan.levels};
     auto add = [&](const DeviceBuffer &b) { k.push_back((uint64_t)(uintptr_t)b.ptr); };
     add(wf.ray[0]); add(wf.ray[1]); add(wf.hit_t); add(wf.hit_body);
     for (int p = 0; p < 2; ++p) { add(wf.sray[p]); add(wf.s_tmax[p]); add(wf.s_ab[p]); add(wf.s_lit[p]); add(wf.lit_bc[p]); add(wf.lit_node[p]); }

@@ -425,6 +425,30 @@ def test_full_size_c4_every_strategy_renders_the_same_frame():
     assert not got[rest].any()
 
 
+def test_origin_hints_change_no_pixel_and_spare_the_exact_tests():
+    """RG_OPT_ORIGIN_HINTS (rg_trace.cuh): k_shade tests every ray it emits against the sphere the ray starts on and
+    the grid tracer skips that sphere.  Same frame, same ray counts, same error counters with the hints on and
+    off and against the verbatim scan (RG_OPT_VERIFY_CULL=2 re-traces every queued ray without hints on the
+    device); far fewer exact tests with them.  C4 (glass, mirrors, diffuse: rays that leave, enter and graze
+    their own sphere) and the all-diffuse C3."""
+    for name, w, h in (("C4", 1280, 720), ("C3", 960, 540)):
+        data, _ = make_scene(name)
+        got = {}
+        for hints in (1, 0):
+            with rg.Scene(data) as sc:
+                sc.set_accel(rg.ACCEL_GRID)
+                sc.set_option(rg._native.OPT_ORIGIN_HINTS, hints)
+                sc.set_option(rg._native.OPT_VERIFY_CULL, 2)     # (host-sized loop + the verbatim re-trace)
+                img = sc.render_image(w, h)
+                assert sc.last_stats.cull_unsound == 0, (name, hints)
+                sc.set_option(rg._native.OPT_VERIFY_CULL, 0)
+                for _ in range(3):                               # host-free loop, then its captured graph
+                    assert np.array_equal(sc.render_image(w, h), img)
+                got[hints] = (img, sc.last_stats)
+        _assert_same(got[1][0], got[0][0], got[1][1], got[0][1], f"{name} hints on vs off")
+        assert got[1][1].exact_tests < 0.85 * got[0][1].exact_tests, (name, got[1][1].exact_tests, got[0][1].exact_tests)
+
+
 def test_resident_brute_kernel_cull_is_sound_at_scale():
     """The shared-memory-resident brute-force kernel (queues of >= 300 k rays, scenes of <= ~11,000
     spheres) with RG_OPT_VERIFY_CULL=1: every pair the FP32 cull rejects is re-tested exactly on the
