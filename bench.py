@@ -352,6 +352,9 @@ def main() -> int:
     ap.add_argument("--e2e-gather", default="host", choices=["host", "device"],
                     help="N>1 end-to-end arm: host = every rank copies its rows over its own PCIe link into ONE pinned "
                          "shared-memory frame; device = gather on rank 0's GPU (--gather) and one D2H from there")
+    ap.add_argument("--e2e-inflight", type=int, default=2,
+                    help="end-to-end arm: steps in flight per GPU (each a complete upload -> render -> frame-to-host step "
+                         "on its own scene handle and host thread; 1 = strictly one after the other)")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config table (test1/2/3, C3, C5)")
     ap.add_argument("--no-in-library", action="store_true", help="skip the in-library multi-GPU arm (N>1)")
     ap.add_argument("--lead", type=float, default=0.6, help="share of a rank's static tiles given to its first in-flight batch")
@@ -563,38 +566,51 @@ def main() -> int:
     if rank == 0:
         value_frame_sha = sha((gathered["frame"] if world > 1 else staging.view(h, w, 4)).cpu().numpy())
 
-    upload_s = [0.0]
-    host_frames = None
+    # Steps in flight.  A step is upload -> render -> frame in host memory -> destroy, each a blocking call of the public
+    # API; a host that renders a sequence of frames keeps the GPU busy during the host-side parts of a step (scene
+    # flattening, the final copy, the synchronisations) by running the next step on a second scene handle from a second
+    # thread.  Every step still does all of its own copies inside the timed region; `ms_per_step` is wall time / steps.
+    e2e_T = max(1, args.e2e_inflight)
+    upload_s = [0.0] * e2e_T
+    host_frames = None          # world > 1: one SharedHostFrame (+ end-of-frame barrier) per in-flight stream of steps
+    e2e_barriers = None
+    host_frame_t = [host_frame] + [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(e2e_T - 1)]
     e2e_gather = args.e2e_gather if world > 1 else "single"
     if world > 1 and args.e2e_gather == "host":
-        from raingun_b200.dist import SharedHostFrame
+        from raingun_b200.dist import HostBarrier, SharedHostFrame
         try:
-            host_frames = SharedHostFrame(w, h, rank, world, tag="e2e")
+            host_frames = [SharedHostFrame(w, h, rank, world, tag=f"e2e{t}") for t in range(e2e_T)]
+            e2e_barriers = [HostBarrier(rank, world, tag=f"e2e{t}") for t in range(e2e_T)]
         except Exception as e:   # /dev/shm or pinning unavailable: every rank falls back together
             print(f"[bench] shared host frame unavailable on rank {rank}: {e}", file=sys.stderr, flush=True)
+            host_frames = None
         ok = torch.tensor([0 if host_frames is None else 1], dtype=torch.int32, device=device)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
-            if host_frames is not None:
-                host_frames.close()
-                host_frames = None
+            host_frames = None
             e2e_gather = "device"
+    if world > 1 and host_frames is None:
+        e2e_T = 1   # the device gather is an NCCL collective: one stream of steps
 
-    def step_e2e():
+    e2e_frame_no = [0] * e2e_T
+
+    def step_e2e(t=0):
         t_up = time.perf_counter()
         sc = rg.Scene(data, device=local_rank)
         sc.set_accel(accel)
-        upload_s[0] += time.perf_counter() - t_up   # reported separately as well
+        upload_s[t] += time.perf_counter() - t_up   # reported separately as well
         if world == 1:
-            r = sc.render_rows_into(w, h, 0, h, host_frame.data_ptr()).rays
+            r = sc.render_rows_into(w, h, 0, h, host_frame_t[t].data_ptr()).rays
             sc.close()
         elif host_frames is not None:
-            # every rank delivers its own rows over its own PCIe link into the one pinned host frame
-            frame_counter[0] += 1
+            # every rank delivers its own rows over its own PCIe link into the one pinned host frame (of stream t)
+            e2e_frame_no[t] += 1
             res = render_frame_sharded(
-                [lambda rows, fptr, sc_=sc: sc_.render_rowlist_host(w, h, rows, fptr)], w, h, rank, world, frame_counter[0], device,
-                tile_rows=args.tile_rows, schedule=args.schedule, gather_mode="host", peer_frames=host_frames, host_barrier=host_barrier)
-            gathered["host_frame"] = res.frame
+                [lambda rows, fptr, sc_=sc: sc_.render_rowlist_host(w, h, rows, fptr)], w, h, rank, world, e2e_frame_no[t], device,
+                tile_rows=args.tile_rows, schedule="static" if e2e_T > 1 else args.schedule, gather_mode="host",
+                peer_frames=host_frames[t], host_barrier=e2e_barriers[t])
+            if t == 0:
+                gathered["host_frame"] = res.frame
             r = sum(s_.rays for s_ in res.stats)
             sc.close()
         else:
@@ -606,27 +622,61 @@ def main() -> int:
                 sc_.close()
         return r
 
-    for _ in range(min(args.warmup, 2)):
-        step_e2e()
-    upload_s[0] = 0.0
+    def e2e_stream(t, nsteps, out):
+        out[t] = sum(step_e2e(t) for _ in range(nsteps))
+
+    def run_e2e(nsteps_total):
+        """nsteps_total steps, dealt round-robin to the in-flight streams (the same split on every rank)."""
+        per = [nsteps_total // e2e_T + (1 if t < nsteps_total % e2e_T else 0) for t in range(e2e_T)]
+        out = [0] * e2e_T
+        if e2e_T == 1:
+            e2e_stream(0, per[0], out)
+        else:
+            import threading
+            th = [threading.Thread(target=e2e_stream, args=(t, per[t], out)) for t in range(e2e_T) if per[t]]
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
+        return sum(out)
+
+    run_e2e(max(min(args.warmup, 2), 1) * e2e_T)
+    for t in range(e2e_T):
+        upload_s[t] = 0.0
     barrier()
     t0 = time.perf_counter()
-    e2e_rays = 0
-    for _ in range(args.steps):
-        e2e_rays += step_e2e()
+    e2e_rays = run_e2e(args.steps)
     barrier()
     e2e_s = reduce_max(time.perf_counter() - t0)
+    # ... and, for the record, the same steps strictly one after the other (the latency of one step)
+    e2e_serial_ms = None
+    if e2e_T > 1:
+        n_serial = max(2, min(args.steps, 6))
+        barrier()
+        t0 = time.perf_counter()
+        out_ = [0] * e2e_T
+        e2e_stream(0, n_serial, out_)
+        barrier()
+        e2e_serial_ms = reduce_max(time.perf_counter() - t0) / n_serial * 1e3
     (e2e_rays,) = reduce_sum([e2e_rays])
     e2e_value = e2e_rays / e2e_s / 1e6 if e2e_s > 0 else 0.0
     e2e_frame_sha = None
     if rank == 0:
         e2e_frame_sha = sha(gathered["host_frame"].numpy() if host_frames is not None else host_frame.numpy())
+        for t in range(1, e2e_T):   # every in-flight stream delivered the same frame
+            other = host_frames[t].array(e2e_frame_no[t]) if host_frames is not None else host_frame_t[t].numpy()
+            if e2e_frame_no[t] or host_frames is None:
+                if sha(other) != e2e_frame_sha:
+                    e2e_frame_sha = "streams differ"
         if e2e_frame_sha != value_frame_sha:
             print(json.dumps({"error": "the end-to-end frame differs from the device-resident frame",
                               "value_frame_sha256": value_frame_sha, "e2e_frame_sha256": e2e_frame_sha}), flush=True)
             return 3
     if host_frames is not None:
-        host_frames.close()
+        for b_ in e2e_barriers:
+            b_.close()
+        for f_ in host_frames:
+            f_.close()
 
     # ---- the same frame rendered on all N GPUs INSIDE the library (rank 0 only; the other ranks idle at the
     # barrier): rg_scene_create_multi + rg_render — what a host without torchrun gets (rendering.rs:27-35)
@@ -740,9 +790,11 @@ def main() -> int:
             "rays_per_frame": rays // max(1, args.steps),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": desc_bytes * world * inflight,
                     "d2h_bytes_per_step": h * w * 4, "ms_per_step": e2e_s / max(1, args.steps) * 1e3,
-                    "scene_upload_ms_per_step": upload_s[0] / max(1, args.steps) * 1e3,
-                    "gather": e2e_gather,
+                    "scene_upload_ms_per_step": sum(upload_s) / max(1, args.steps) * 1e3,
+                    "scene_upload_note": "wall time of rg_scene_create per step; with steps in flight it includes waiting for the GPU, which is rendering the other step",
+                    "gather": e2e_gather, "steps_in_flight": e2e_T, "ms_per_step_one_in_flight": e2e_serial_ms,
                     "what": "rg_scene_create (scene H2D) + render + RGBA8 frame D2H into pinned host memory + rg_scene_destroy, per step"
+                            + (f"; {e2e_T} steps in flight per GPU (each on its own scene handle and host thread), ms_per_step = wall time / steps" if e2e_T > 1 else "")
                             + ("; N>1: every rank copies its rows into ONE pinned shared-memory frame over its own PCIe link" if e2e_gather == "host" else "")},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "brute_force": brute,
             # the kernel that dominates the `value` arm is latency / issue bound, not FP32- or HBM-bound: its
