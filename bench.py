@@ -352,7 +352,12 @@ def main() -> int:
     ap.add_argument("--e2e-gather", default="host", choices=["host", "device"],
                     help="N>1 end-to-end arm: host = every rank copies its rows over its own PCIe link into ONE pinned "
                          "shared-memory frame; device = gather on rank 0's GPU (--gather) and one D2H from there")
-    ap.add_argument("--e2e-inflight", type=int, default=2,
+    ap.add_argument("--frames-inflight", type=int, default=1,
+                    help="device-resident arm: frames in flight per GPU (each on its own scene handle(s), host thread, frame "
+                         "buffers and end-of-frame barrier); 1 (default) = one frame after the other, ms_per_step is then the "
+                         "latency of a frame.  Measured on 8 B200: 2.817 / 2.788 / 2.785 ms per frame with 1 / 2 / 3 in flight - "
+                         "the device-resident arm is bound on the GPUs, not by the host between frames")
+    ap.add_argument("--e2e-inflight", type=int, default=3,
                     help="end-to-end arm: steps in flight per GPU (each a complete upload -> render -> frame-to-host step "
                          "on its own scene handle and host thread; 1 = strictly one after the other)")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config table (test1/2/3, C3, C5)")
@@ -489,8 +494,8 @@ def main() -> int:
             host_barrier.close()
             host_barrier = None
 
-    def lane_renderers(lanes):
-        if peer_frames is not None:
+    def lane_renderers(lanes, peer):
+        if peer is not None:
             return [(lambda rows, fptr, sc_=sc_, st_=st_: sc_.render_rowlist_scatter(w, h, rows, fptr, st_))
                     for sc_, st_ in lanes]
         return [(lambda rows, out, sc_=sc_, st_=st_: sc_.render_rowlist_device(w, h, rows, out.data_ptr(), st_))
@@ -500,47 +505,89 @@ def main() -> int:
     staging = torch.empty((h * w * 4,), dtype=torch.uint8, device=device)
     frame_buf = torch.empty((h, w, 4), dtype=torch.uint8, device=device) if world > 1 else None
     host_frame = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()
-    frame_counter = [0]
 
     gathered = {}
 
-    def step_resident(lanes_):
+    # Frames in flight.  A frame is one blocking call of the public API per rank plus the end-of-frame barrier; a host
+    # that renders a SEQUENCE of frames hides the host-side part of a frame (launch, the final synchronisation, the
+    # barrier and the skew between the ranks) behind the next frame by driving it from a second thread on its own scene
+    # handle, frame buffers and barrier.  Every frame is still rendered completely; ms_per_step is wall time / frames and
+    # the latency of a frame is reported beside it (frame_latency_ms).  With a collective gather (NCCL) frames go one by one.
+    F = max(1, args.frames_inflight)
+    if world > 1 and (peer_frames is None or host_barrier is None):
+        F = 1
+    ctxs = [{"lanes": lanes, "peer": peer_frames, "bar": host_barrier, "staging": staging, "frame_no": 0, "id": 0}]
+    for f in range(1, F):
+        sc_f = rg.Scene(data, device=local_rank)
+        sc_f.set_accel(accel)
+        peer_f = bar_f = None
+        if world > 1:
+            from raingun_b200.dist import HostBarrier, PeerFrames
+            peer_f = PeerFrames(w, h, rank, world, local_rank, tag=f"v{f}")
+            bar_f = HostBarrier(rank, world, tag=f"v{f}")
+        ctxs.append({"lanes": make_lanes(sc_f), "peer": peer_f, "bar": bar_f, "frame_no": 0, "id": f,
+                     "staging": torch.empty((h * w * 4,), dtype=torch.uint8, device=device)})
+
+    def step_resident(ctx):
         """One frame, inputs (scene) and output resident in HBM.  Returns (rays, launches, stats)."""
         if world == 1:
-            st = lanes_[0][0].render_rows_device(w, h, 0, h, staging.data_ptr(), sptr)
+            st = ctx["lanes"][0][0].render_rows_device(w, h, 0, h, ctx["staging"].data_ptr(), sptr)
             return st.rays, st.gpu_launches, st
-        frame_counter[0] += 1
+        ctx["frame_no"] += 1
         res = render_frame_sharded(
-            lane_renderers(lanes_), w, h, rank, world,
-            frame_counter[0], device, tile_rows=args.tile_rows, schedule=args.schedule, staging=staging,
-            gather_mode=args.gather, frame_buf=frame_buf, lead=args.lead, peer_frames=peer_frames, host_barrier=host_barrier)
-        gathered["frame"] = res.frame   # rank 0: the gathered (H, W, 4) frame in HBM
-        gathered["schedule"] = res.schedule
+            lane_renderers(ctx["lanes"], ctx["peer"]), w, h, rank, world,
+            ctx["frame_no"], device, tile_rows=args.tile_rows, schedule=args.schedule if F == 1 else "static", staging=ctx["staging"],
+            gather_mode=args.gather, frame_buf=frame_buf, lead=args.lead, peer_frames=ctx["peer"], host_barrier=ctx["bar"])
+        if ctx["id"] == 0:
+            gathered["frame"] = res.frame   # rank 0: the gathered (H, W, 4) frame in HBM
+            gathered["schedule"] = res.schedule
         return (sum(s.rays for s in res.stats), sum(s.gpu_launches for s in res.stats),
                 res.stats[-1] if res.stats else None)
 
+    def run_frames(n_total, acc):
+        """n_total frames dealt to the F in-flight streams (the same split on every rank); acc collects per stream
+        (rays, launches, last stats, per-frame wall seconds)."""
+        per = [n_total // F + (1 if f < n_total % F else 0) for f in range(F)]
+
+        def body(f):
+            rays_ = launches_ = 0
+            last_ = None
+            lat = []
+            for _ in range(per[f]):
+                t_ = time.perf_counter()
+                r_, l_, last_ = step_resident(ctxs[f])
+                lat.append(time.perf_counter() - t_)
+                rays_ += r_
+                launches_ += l_
+            acc[f] = (rays_, launches_, last_, lat)
+        if F == 1:
+            body(0)
+        else:
+            import threading
+            th = [threading.Thread(target=body, args=(f,)) for f in range(F)]
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
+
     # ---- device-resident arm: `value`
-    for _ in range(args.warmup):
-        step_resident(lanes)
+    run_frames(args.warmup * F, [None] * F)
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    rays = launches = 0
-    last_stats = None
-    marks = [e0]
-    for _ in range(args.steps):
-        r, l, last_stats = step_resident(lanes)
-        rays += r
-        launches += l
-        marks.append(torch.cuda.Event(enable_timing=True))
-        marks[-1].record(stream)
+    acc = [None] * F
+    run_frames(args.steps, acc)
     e1.record(stream)
     barrier()
     ms_total = reduce_max(e0.elapsed_time(e1))
-    step_ms = [a.elapsed_time(b) for a, b in zip(marks, marks[1:])]   # this rank's view of each step (SURVEY 8d: median)
+    rays = sum(a_[0] for a_ in acc if a_)
+    launches = sum(a_[1] for a_ in acc if a_)
+    last_stats = acc[0][2]
+    step_ms = [x * 1e3 / F for a_ in acc if a_ for x in a_[3]]   # this rank's view of each frame's share of the wall clock
+    frame_latency_ms = float(np.median([x * 1e3 for a_ in acc if a_ for x in a_[3]]))
     clocks = sampler.stop() if rank == 0 else None
     rays, launches = reduce_sum([rays, launches])
     ms_per_step = ms_total / max(1, args.steps)
@@ -553,8 +600,15 @@ def main() -> int:
         data.body_kind, data.body_geom, data.coloration_kind, data.color, data.texture_id, data.texture_offset,
         data.albedo, data.surface_kind, data.surface_param, data.light_kind, data.light_vec, data.light_color,
         data.light_intensity)) + sum(t.nbytes for t in data.textures))
-    for sc_, _ in lanes:
-        sc_.close()
+    for ctx in ctxs:
+        for sc_, _ in ctx["lanes"]:
+            sc_.close()
+    for ctx in ctxs[1:]:   # the extra in-flight streams' frames and barriers (collective closes: same order on every rank)
+        if ctx["peer"] is not None:
+            ctx["peer"].close()
+        if ctx["bar"] is not None:
+            ctx["bar"].close()
+        ctx["staging"] = None
 
     import hashlib
 
@@ -615,7 +669,8 @@ def main() -> int:
             sc.close()
         else:
             ls = make_lanes(sc)            # every lane re-uploads the scene (counted in h2d_bytes_per_step)
-            r, _, _ = step_resident(ls)    # row tiles gathered on rank 0's GPU
+            ctxs[0]["lanes"] = ls
+            r, _, _ = step_resident(ctxs[0])    # row tiles gathered on rank 0's GPU
             if rank == 0:
                 host_frame.copy_(gathered["frame"])
             for sc_, _ in ls:
@@ -781,12 +836,14 @@ def main() -> int:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "ms_per_step_median": statistics.median(step_ms) if step_ms else None,
+            "frames_in_flight": F, "frame_latency_ms": frame_latency_ms,
             "higher_is_better": True, "scaling": "strong",   # one fixed frame split N ways
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.workload, spec, data, {
                 "accel": accel_used, "pipeline": "wavefront",
                 "parallelism": f"row-tiles x{world} ({args.schedule}->{gathered.get('schedule', '?')}, {args.tile_rows}-row tiles, {inflight} batches in flight per GPU, gather={args.gather}, end-of-frame barrier={'shared memory' if host_barrier is not None else 'nccl'})" if world > 1 else "1 GPU",
-                "l2": "per-frame working set (ray queues + nodes, several GB) exceeds the 126 MB L2; no explicit flush"}),
+                "l2": "per-frame working set (ray queues + nodes, several GB) exceeds the 126 MB L2; no explicit flush",
+                "frames_in_flight": f"{F} per GPU (own scene handle, host thread, frame buffers and end-of-frame barrier each): ms_per_step = wall time / frames; frame_latency_ms = one frame, start to end"}),
             "rays_per_frame": rays // max(1, args.steps),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": desc_bytes * world * inflight,
                     "d2h_bytes_per_step": h * w * 4, "ms_per_step": e2e_s / max(1, args.steps) * 1e3,
