@@ -204,7 +204,7 @@ k_trace_brute(const DScene s, const TraceArgs a) {
     static_assert(R * kTraceThreads <= (1 << kSlotBits), "slot bits");
     static_assert(U == 2 || U == 4, "U spheres = U/2 pairs per iteration");
     static_assert(kCullPad % U == 0 && U <= kCullPad, "records are padded to kCullPad");
-    __shared__ __align__(128) float4 stage[2][kChunkSpheres + kCullPad];   // + slack for the prefetch
+    __shared__ __align__(128) float4 stage[2][kChunkSpheres + 3 * kCullPad];   // + slack for the prefetch (two groups ahead)
     __shared__ uint64_t mbar[2];
     __shared__ uint32_t cq[kTraceWarps][64];
     __shared__ double best_t[R * kTraceThreads];
@@ -361,35 +361,80 @@ k_trace_brute(const DScene s, const TraceArgs a) {
                 }
             }
         };
-        // Hot loop.  The "did anything survive" vote of group j is taken one iteration late, so
-        // the FSETP -> VOTE -> BRA latency chain overlaps the next group's FFMAs instead of
-        // stalling the warp at the bottom of every iteration.
-        float4 sv[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) sv[u] = sp[u];
-        bool prev_pass = false;
-#pragma unroll 1
-        for (uint32_t j = 0; j < cnt; j += U) {
-            float4 sc[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) sc[u] = sv[u];
-            // software prefetch of the next U records (the stage has kCullPad records of slack)
-#pragma unroll
-            for (int u = 0; u < U; ++u) sv[u] = sp[j + U + u];
-            const bool vote_prev = __any_sync(0xffffffffu, prev_pass);
-            bool any_pass = a.verify != 0;
+        // Hot loop: the software-pipelined form of k_trace_brute_resident (see there): one reject predicate per group from
+        // NaN-propagating maxima, the h values kept in registers for the rare survivor, records addressed by their
+        // shared-window address, a group's vote + branch issued behind the next group's FFMA2s.
+        auto enqueue = [&](bool pass, uint32_t sph, uint32_t slot) {
+            const uint32_t mask = __ballot_sync(0xffffffffu, pass);
+            if (mask) {
+                if (pass) cq[warp][qn + __popc(mask & lanemask_lt)] = (sph << kSlotBits) | slot;
+                qn += __popc(mask);
+                __syncwarp();
+                if (qn >= 32u) {
+                    drain(qn - 32u, 32u);
+                    qn -= 32u;
+                    __syncwarp();
+                }
+            }
+        };
+        auto test_group = [&](const float4 (&sc)[U], float2 (&hh)[R][U / 2]) -> bool {
+            bool all_rej = true;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
 #pragma unroll
                 for (int u = 0; u < U; u += 2) {
-                    const float2 h = cull_h2(cr[r], sc[u], sc[u + 1]);
-                    any_pass = any_pass | !(h.x < cr[r].nthr) | !(h.y < cr[r].nthr);   // `|`: no short-circuit branches
+                    hh[r][u / 2] = cull_h2(cr[r], sc[u], sc[u + 1]);
+                    all_rej = all_rej & (max_nan(hh[r][u / 2].x, hh[r][u / 2].y) < cr[r].nthr);
                 }
             }
-            if (vote_prev) survivors(j - U);
-            prev_pass = any_pass;
+            return !all_rej;
+        };
+        auto collect = [&](const float2 (&hh)[R][U / 2], uint32_t j) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                bool pass_r = false;
+#pragma unroll
+                for (int u = 0; u < U; u += 2) pass_r = pass_r | !(hh[r][u / 2].x < cr[r].nthr) | !(hh[r][u / 2].y < cr[r].nthr);
+                if (__any_sync(0xffffffffu, pass_r)) {
+                    const uint32_t slot = r * kTraceThreads + tid;
+                    const bool live = block_base + slot < n_rays;
+#pragma unroll
+                    for (int u = 0; u < U; u += 2) {
+                        const uint32_t sph = sph_base + j + u;
+                        enqueue(live && sph < nsph && !(hh[r][u / 2].x < cr[r].nthr), sph, slot);
+                        enqueue(live && sph + 1 < nsph && !(hh[r][u / 2].y < cr[r].nthr), sph + 1, slot);
+                    }
+                }
+            }
+        };
+        if (a.verify) {   // debug form of the loop: every culled pair is re-tested exactly (survivors())
+#pragma unroll 1
+            for (uint32_t j = 0; j < cnt; j += U) survivors(j);
+        } else {
+            uint32_t saddr = smem_u32(sp);
+            float4 s0[U], s1[U];
+            float2 hA[R][U / 2], hB[R][U / 2];
+            bool fB = false;
+            uint32_t jB = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) s0[u] = lds128(saddr + 16u * u);
+#pragma unroll 1
+            for (uint32_t j = 0; j < cnt; j += 2 * U, saddr += 32u * U) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) s1[u] = lds128(saddr + 16u * (U + u));       // (the stage has 3 kCullPad records of slack)
+                const bool fA = test_group(s0, hA);
+                if (__any_sync(0xffffffffu, fB)) collect(hB, jB);                        // the previous turn's second group
+                fB = false;
+                if (j + U < cnt) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) s0[u] = lds128(saddr + 16u * (2 * U + u));
+                    fB = test_group(s1, hB);
+                    jB = j + U;
+                }
+                if (__any_sync(0xffffffffu, fA)) collect(hA, j);
+            }
+            if (__any_sync(0xffffffffu, fB)) collect(hB, jB);
         }
-        if (cnt && __any_sync(0xffffffffu, prev_pass)) survivors(cnt - U);
         __syncthreads();   // everyone is done with stage[st] before it is refilled
     }
     if (qn) drain(0u, qn);

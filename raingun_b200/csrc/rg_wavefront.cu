@@ -522,7 +522,8 @@ static int launch_trace(rg_scene *sc, const TraceArgs &ta, bool use_grid, cudaSt
                 case 6: RG_LAUNCH_BRUTE(4, 2, 3); break;
                 case 7: RG_LAUNCH_BRUTE(4, 4, 3); break;
                 case 8: RG_LAUNCH_BRUTE(4, 2, 2); break;
-                default: RG_LAUNCH_BRUTE(2, 4, 4); break;
+                case 9: RG_LAUNCH_BRUTE(2, 4, 4); break;
+                default: RG_LAUNCH_BRUTE(4, 2, 2); break;   // with round 2's loop (C4, streaming kernel only): 366 ms; (2,4,3) 375, (2,4,4) 386, (4,4,2) 405
             }
         } else if (ta.n >= full * 2 * 2) {
             RG_LAUNCH_BRUTE(2, 4, 4);
