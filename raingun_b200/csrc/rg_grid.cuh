@@ -39,7 +39,11 @@
 
 namespace rg {
 
-constexpr int kGridTraceThreads = 128;
+#ifndef RG_GRID_THREADS
+#define RG_GRID_THREADS 32    // warps of a CTA share nothing: the size only sets how finely finished CTAs make room for the
+                              // next kernel's (measured 256 / 128 / 64 / 32 threads: C4 18.94 / 18.02 / 17.98 / 17.82 ms)
+#endif
+constexpr int kGridTraceThreads = RG_GRID_THREADS;
 constexpr float kGridInflate = 2e-3f;       // in cells; see above
 constexpr float kGridMaxCoord = 2048.0f;    // |grid coordinate| limit for FP32 traversal
 constexpr double kGridUnitTol = 1e-9;
@@ -47,7 +51,7 @@ constexpr int kGridRefill = 12;             // refill when at least this many la
 constexpr int kGridExactQuorum = 6;         // evaluate pending candidates when this many lanes wait
 constexpr int kGridScanBurst = 4;           // scan steps between quorum checks
 #ifndef RG_GRID_MINB
-#define RG_GRID_MINB 7   // CTAs per SM the register budget is set for (72 registers; measured 4..8)
+#define RG_GRID_MINB (7 * 128 / RG_GRID_THREADS)   // CTAs per SM the register budget is set for: 28 warps per SM = 72 registers (measured 16..32 warps)
 #endif
 constexpr uint32_t kNoSphere = 0xFFFFFFFFu;
 constexpr float kFltBig = 3.4e38f;

@@ -24,7 +24,7 @@ for wl in sys.argv[1:]:
     print(f"  {wl}: {best:8.3f} ms  {st.rays / best / 1e3:7.0f} Mrays/s  exact {st.exact_tests}  crc {crc:08x}", flush=True)
     sc.close()
 '''
-variants = sys.argv[1:] or ["default:6"]
+variants = sys.argv[1:] or ["default:"]   # name:RG_GRID_BPS (blocks of 32 threads per SM; empty = the library default, 28):ENV=value,...
 wls = os.environ.get("AB_WORKLOADS", "C3 C4").split()
 for v in variants:
     name, _, rest = v.partition(":")
