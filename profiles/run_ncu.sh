@@ -27,6 +27,7 @@ $FRAME > /dev/null 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_shade -s 11 -c 1 \
     -o gpurun_out/prof_shade_${TAG} -f $FRAME > gpurun_out/ncu_shade_${TAG}.log 2>&1
 echo "shade capture rc=$?"
+if [ "${SKIP_BRUTE:-0}" != "0" ]; then du -sh gpurun_out; exit 0; fi   # (gpurun brings back at most 64 MiB: three captures can exceed it)
 BRUTE="python tools/gpu_brute.py C4"
 $BRUTE > /dev/null 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_trace_brute -s 0 -c 2 \
