@@ -494,6 +494,24 @@ def main() -> int:
             host_barrier.close()
             host_barrier = None
 
+    def run_threads(jobs):
+        """Runs the callables on one thread each; an exception in any of them is re-raised here (not lost with its thread)."""
+        import threading
+        errors = []
+
+        def guarded(job):
+            try:
+                job()
+            except BaseException as e:   # noqa: BLE001 - reported below
+                errors.append(e)
+        th = [threading.Thread(target=guarded, args=(j,)) for j in jobs]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        if errors:
+            raise errors[0]
+
     def lane_renderers(lanes, peer):
         if peer is not None:
             return [(lambda rows, fptr, sc_=sc_, st_=st_: sc_.render_rowlist_scatter(w, h, rows, fptr, st_))
@@ -563,12 +581,7 @@ def main() -> int:
         if F == 1:
             body(0)
         else:
-            import threading
-            th = [threading.Thread(target=body, args=(f,)) for f in range(F)]
-            for x in th:
-                x.start()
-            for x in th:
-                x.join()
+            run_threads([lambda f=f: body(f) for f in range(F)])
 
     # ---- device-resident arm: `value`
     run_frames(args.warmup * F, [None] * F)
@@ -687,12 +700,7 @@ def main() -> int:
         if e2e_T == 1:
             e2e_stream(0, per[0], out)
         else:
-            import threading
-            th = [threading.Thread(target=e2e_stream, args=(t, per[t], out)) for t in range(e2e_T) if per[t]]
-            for x in th:
-                x.start()
-            for x in th:
-                x.join()
+            run_threads([lambda t=t: e2e_stream(t, per[t], out) for t in range(e2e_T) if per[t]])
         return sum(out)
 
     run_e2e(max(min(args.warmup, 2), 1) * e2e_T)
