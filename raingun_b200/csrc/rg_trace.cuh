@@ -6,7 +6,8 @@
 //     (cp.async.bulk + mbarrier, double-buffered), one 16-byte FP32 cull record per sphere;
 //   * each thread owns R rays (register-tiled), so one broadcast LDS.128 feeds 32*R tests;
 //   * a test is a CONSERVATIVE reject in FP32 (rg_cull.h); two spheres are tested per
-//     instruction with Blackwell's packed FFMA2 (fma.rn.f32x2): 7 FFMA2 + 2 FSETP per pair;
+//     instruction with Blackwell's packed FFMA2 (fma.rn.f32x2): 7 FFMA2 + one FMNMX.NAN + one FSETP per
+//     ray and sphere pair; the loop is software-pipelined by hand (see k_trace_brute_resident);
 //   * the rare survivors are not evaluated in the divergent inner loop: they are appended
 //     to a per-warp candidate queue with __ballot_sync/__popc and evaluated 32 at a time,
 //     one candidate per lane, with the reference's exact FP64 test (rg_exact.cuh);
